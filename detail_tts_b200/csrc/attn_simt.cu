@@ -1,0 +1,120 @@
+// attn_simt.cu -- exact-fp32 attention on CUDA cores, one (query, head, utterance) per CTA.
+// Covers every small attention on the path with one kernel:
+//   GPT-2 causal attention, prefill and KV-cache decode  (transformers modeling_gpt2.py:54-72)
+//   MelStyleEncoder 2-head attention, temperature sqrt(d_model)  (vqvae/modules/modules.py:565-639)
+//   enc_p windowed relative-position attention  (vqvae/modules/attentions.py:198-239; closed form in
+//     SURVEY.md Appendix D6)
+//   contextual_embedder / latent_conditioner / SIMT check of the diffusion AttentionBlock
+//     (vqvae/utils/diff_util.py:145-169, xtransformers.py:177-186)
+#include "common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_simt_kernel(const dtts_attention_params p) {
+  extern __shared__ float sm[];
+  __shared__ float red[40];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (i >= p.q_len[b]) return;
+  const int hd = p.head_dim;
+  int nk = p.k_len[b];
+  if (p.causal) {
+    int lim = i + (p.causal_offset ? p.causal_offset[b] : 0) + 1;
+    nk = lim < nk ? lim : nk;
+  }
+  if (nk <= 0) return;
+  float* qs = sm;                 // [hd]
+  float* sc = sm + hd;            // [nk]
+  float* part = sc + nk;          // [JP*hd]
+  const T* q = (const T*)p.q + (long)(p.q_off[b] + i) * p.ldq + (long)h * p.head_stride_q;
+  const T* kb = (const T*)p.k + (long)p.k_off[b] * p.ldk + (long)h * p.head_stride_k;
+  const T* vb = (const T*)p.v + (long)p.k_off[b] * p.ldv + (long)h * p.head_stride_v;
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) qs[d] = ldf<T>(q + d) * p.scale;
+  __syncthreads();
+  // scores
+  float lmax = -INFINITY;
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    const T* kj = kb + (long)j * p.ldk;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(qs[d], ldf<T>(kj + d), s);
+    if (p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE) {
+      int r = j - i;
+      r = r < -p.bias_half ? -p.bias_half : (r > p.bias_half ? p.bias_half : r);
+      s += p.bias_table[h * (2 * p.bias_half + 1) + r + p.bias_half];
+    } else if (p.bias_mode == DTTS_ATTN_BIAS_WINDOW_REL) {
+      int r = j - i;
+      if (r >= -p.window && r <= p.window) {
+        const float* ek = p.rel_k + (r + p.window) * hd;
+        float t = 0.f;
+        for (int d = 0; d < hd; ++d) t = fmaf(qs[d], ek[d], t);
+        s += t;
+      }
+    }
+    sc[j] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  const float mx = block_max(lmax, red);
+  float lsum = 0.f;
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    lsum += e;
+  }
+  const float inv = 1.0f / block_sum(lsum, red);  // also orders the sc[] writes before the reads below
+  // output: thread (jp, d)
+  const int JP = blockDim.x / hd;
+  const int d = threadIdx.x % hd, jp = threadIdx.x / hd;
+  float o = 0.f;
+  if (jp < JP) {
+    for (int j = jp; j < nk; j += JP) o = fmaf(sc[j], ldf<T>(vb + (long)j * p.ldv + d), o);
+    if (p.bias_mode == DTTS_ATTN_BIAS_WINDOW_REL && jp == 0) {
+      for (int r = -p.window; r <= p.window; ++r) {
+        int j = i + r;
+        if (j >= 0 && j < nk) o = fmaf(sc[j], p.rel_v[(r + p.window) * hd + d], o);
+      }
+    }
+    part[jp * hd + d] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x < hd) {
+    float t = 0.f;
+    for (int q_ = 0; q_ < JP; ++q_) t += part[q_ * hd + threadIdx.x];
+    t *= inv;
+    const long orow = p.q_off[b] + i;
+    if (p.out_f32) p.out_f32[orow * p.ldo32 + h * hd + threadIdx.x] = t;
+    if (p.out_f16) ((__half*)p.out_f16)[orow * p.ldo16 + h * hd + threadIdx.x] = __float2half_rn(t);
+  }
+}
+
+}  // namespace
+
+extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->q && p->k && p->v && p->q_off && p->q_len && p->k_off && p->k_len, "attention_f32: null argument");
+  DTTS_REQUIRE(p->head_dim > 0 && p->head_dim <= 256, "attention_f32: head_dim out of range");
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "attention_f32: no output");
+  DTTS_REQUIRE(p->max_q_len > 0 && p->n_utt > 0 && p->n_heads > 0, "attention_f32: empty problem");
+  DTTS_REQUIRE(p->bias_mode != DTTS_ATTN_BIAS_RELPOS_TABLE || p->bias_table, "attention_f32: missing bias table");
+  DTTS_REQUIRE(p->bias_mode != DTTS_ATTN_BIAS_WINDOW_REL || (p->rel_k && p->rel_v), "attention_f32: missing rel embeddings");
+  static int max_smem = 0;
+  if (!max_smem) {
+    max_smem = 200 * 1024;
+    cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(attention_simt_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  }
+  DTTS_REQUIRE(p->max_k_len > 0, "attention_f32: max_k_len must be set");
+  const int threads = 256;
+  const size_t smem = (size_t)(p->head_dim + p->max_k_len + threads) * sizeof(float);
+  DTTS_REQUIRE(smem <= (size_t)max_smem, "attention_f32: too many keys for one CTA (%d)", p->max_k_len);
+  dim3 grid(p->max_q_len, p->n_heads, p->n_utt);
+  if (p->is_f16)
+    attention_simt_kernel<__half><<<grid, threads, smem, (cudaStream_t)stream>>>(*p);
+  else
+    attention_simt_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("attention_simt");
+  return 0;
+}

@@ -1,0 +1,198 @@
+// norm.cu -- GroupNorm32 (+FiLM +SiLU) per utterance and row LayerNorm.
+//   GroupNorm: vqvae/utils/diff_util.py:113-133 (fp32 stats over channels-in-group x frames),
+//              vqvae/diff_model.py:107,113-115 (scale-shift norm), :242 (code_norm FiLM).
+//   LayerNorm: HF GPT2Block ln_1/ln_2/ln_f, gpt/model.py:322, vqvae/modules/modules.py:36-48.
+// GroupNorm is HBM/L2-bound: one CTA owns (utterance, 4 groups); the strip is read once from
+// global into shared memory (when it fits), statistics are two-pass exact (mean, then centred
+// variance) and the normalised fp16 GEMM operand is written straight from shared memory.
+#include "common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __half2 a = *reinterpret_cast<__half2*>(&u.x), b = *reinterpret_cast<__half2*>(&u.y);
+  float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+constexpr int GN_GROUPS_PER_CTA = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(384)
+groupnorm_kernel(const T* __restrict__ x, int ldx, int C, int cpg, const int* __restrict__ utt_off,
+                 const int* __restrict__ utt_len, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ film_scale, const float* __restrict__ film_shift, int ld_film,
+                 const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
+                 __half* __restrict__ out16, int ldo16, int cache_rows) {
+  extern __shared__ float4 cache[];  // [cache_rows][Q]
+  __shared__ float red[40];
+  const int b = blockIdx.y;
+  const int cw = GN_GROUPS_PER_CTA * cpg;  // channels per CTA
+  const int c0 = blockIdx.x * cw;
+  const int Q = cw >> 2;                   // float4 columns per row
+  const int rs = blockDim.x / Q;           // rows per sweep
+  const int col4 = threadIdx.x % Q;
+  const int rsub = threadIdx.x / Q;
+  const bool active = rsub < rs;
+  const int g = (col4 * 4) / cpg;          // group of this thread (static)
+  const int T_ = utt_len[b];
+  const long row0 = utt_off[b];
+  const T* xb = x + row0 * ldx + c0 + col4 * 4;
+
+  // pass 1: sum (and fill the cache)
+  float s = 0.f;
+  if (active)
+    for (int r = rsub; r < T_; r += rs) {
+      float4 v = load4<T>(xb + (long)r * ldx);
+      if (r < cache_rows) cache[r * Q + col4] = v;
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  float mean_g[GN_GROUPS_PER_CTA];
+#pragma unroll
+  for (int i = 0; i < GN_GROUPS_PER_CTA; ++i) mean_g[i] = block_sum((active && g == i) ? s : 0.f, red) / ((float)T_ * cpg);
+  const float mean = mean_g[0] * (g == 0) + mean_g[1] * (g == 1) + mean_g[2] * (g == 2) + mean_g[3] * (g == 3);
+  // pass 2: centred sum of squares
+  float ss = 0.f;
+  if (active)
+    for (int r = rsub; r < T_; r += rs) {
+      float4 v = r < cache_rows ? cache[r * Q + col4] : load4<T>(xb + (long)r * ldx);
+      float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  float rstd_g[GN_GROUPS_PER_CTA];
+#pragma unroll
+  for (int i = 0; i < GN_GROUPS_PER_CTA; ++i)
+    rstd_g[i] = rsqrtf(block_sum((active && g == i) ? ss : 0.f, red) / ((float)T_ * cpg) + eps);
+  const float rstd = rstd_g[0] * (g == 0) + rstd_g[1] * (g == 1) + rstd_g[2] * (g == 2) + rstd_g[3] * (g == 3);
+  if (!active) return;
+  // pass 3: normalise + affine (+FiLM) (+SiLU)
+  const int c = c0 + col4 * 4;
+  float ga[4], be[4], fs[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { ga[q] = gamma[c + q]; be[q] = beta[c + q]; }
+  if (film_scale) {
+    const long fr = film_idx ? film_idx[b] : b;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { fs[q] = film_scale[fr * ld_film + c + q]; fb[q] = film_shift[fr * ld_film + c + q]; }
+  }
+  // fold: y = ((x-mean)*rstd*ga + be)*(1+fs) + fb = x*A + B
+  float A_[4], B_[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    A_[q] = rstd * ga[q];
+    B_[q] = be[q] - mean * A_[q];
+  }
+  for (int r = rsub; r < T_; r += rs) {
+    float4 v = r < cache_rows ? cache[r * Q + col4] : load4<T>(xb + (long)r * ldx);
+    float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t = y[q] * A_[q] + B_[q];
+      if (film_scale) t = t * (1.0f + fs[q]) + fb[q];
+      if (act == DTTS_ACT_SILU) t = t * sigmoidf_(t);
+      y[q] = t;
+    }
+    const long orow = row0 + r;
+    if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(out16 + orow * ldo16 + c) = pk;
+    }
+  }
+}
+
+constexpr int LN_MAXE = 32;  // C <= 1024
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, const float* __restrict__ res, int ldr,
+                 float* __restrict__ out32, int ldo32, __half* __restrict__ out16, int ldo16) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[LN_MAXE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) {
+    const int c = lane + 32 * i;
+    float t = 0.f;
+    if (c < C) {
+      t = x[(long)row * ldx + c];
+      if (res) t += res[(long)row * ldr + c];
+    }
+    v[i] = t;
+    s += t;
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) { float d = v[i] - mean; ss += d * d; }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (out32) out32[(long)row * ldo32 + c] = y;
+      if (out16) out16[(long)row * ldo16 + c] = __float2half_rn(y);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->x && p->gamma && p->beta && p->utt_off && p->utt_len, "groupnorm: null argument");
+  DTTS_REQUIRE(p->groups > 0 && p->C % p->groups == 0, "groupnorm: C %% groups != 0");
+  const int cpg = p->C / p->groups;
+  DTTS_REQUIRE(p->groups % GN_GROUPS_PER_CTA == 0 && cpg % 4 == 0, "groupnorm: needs groups %% 4 == 0 and channels/group %% 4 == 0");
+  const int Q = GN_GROUPS_PER_CTA * cpg / 4;
+  DTTS_REQUIRE(Q <= 384, "groupnorm: channels per group too large");
+  DTTS_REQUIRE(p->ldx % 4 == 0 && (!p->out_f32 || p->ldo32 % 4 == 0) && (!p->out_f16 || p->ldo16 % 4 == 0), "groupnorm: leading dims must be multiples of 4");
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "groupnorm: no output");
+  DTTS_REQUIRE(p->act == DTTS_ACT_NONE || p->act == DTTS_ACT_SILU, "groupnorm: unsupported activation");
+  static int max_smem = 0;
+  if (!max_smem) {
+    max_smem = 160 * 1024;
+    cudaFuncSetAttribute(groupnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(groupnorm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  }
+  // cache as many rows as fit; the caller passes the longest utterance via utt_len on device, so
+  // size for the budget (rows beyond cache_rows are re-read from L2).
+  const int row_bytes = Q * 16;
+  int cache_rows = max_smem / row_bytes;
+  if (p->max_len > 0 && p->max_len < cache_rows) cache_rows = p->max_len;
+  dim3 grid(p->groups / GN_GROUPS_PER_CTA, p->n_utt);
+  const int threads = (384 / Q) * Q;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->x_is_f16)
+    groupnorm_kernel<__half><<<grid, threads, cache_rows * row_bytes, st>>>(
+        (const __half*)p->x, p->ldx, p->C, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
+        p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16, cache_rows);
+  else
+    groupnorm_kernel<float><<<grid, threads, cache_rows * row_bytes, st>>>(
+        (const float*)p->x, p->ldx, p->C, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
+        p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16, cache_rows);
+  DTTS_CHECK_LAUNCH("groupnorm");
+  return 0;
+}
+
+extern "C" int dtts_layernorm(const dtts_layernorm_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->x && p->gamma && p->beta, "layernorm: null argument");
+  DTTS_REQUIRE(p->C > 0 && p->C <= 32 * LN_MAXE, "layernorm: C out of range");
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "layernorm: no output");
+  if (p->M <= 0) return 0;
+  const int rows_per_cta = 8;
+  layernorm_kernel<<<ceil_div(p->M, rows_per_cta), rows_per_cta * 32, 0, (cudaStream_t)stream>>>(
+      p->x, p->ldx, p->M, p->C, p->gamma, p->beta, p->eps, p->res, p->ldr, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
+  DTTS_CHECK_LAUNCH("layernorm");
+  return 0;
+}

@@ -1,0 +1,221 @@
+// sampling.cu -- the per-token host-free tail of the GPT decode step.
+//   dtts_process_logits: HF processor chain RepetitionPenalty -> Temperature -> TopK -> TopP ->
+//     softmax (or argmax when greedy): transformers generation/logits_process.py:298,407-410,
+//     522-532,582-585, as configured by vqvae/model_24k.py:782-792 / gpt/model.py:540-544.
+//   dtts_append_token: HF _sample bookkeeping (generation/utils.py:2797-2805) fused with the next
+//     step's input embedding mel_embedding[id] + mel_pos_embedding[pos] (gpt/model.py:145-148).
+// One CTA per utterance row; the 8194-entry logits row lives in shared memory for the whole chain
+// (read once from HBM, dense probabilities written once).  Top-k uses an exact 4-pass radix select
+// on order-preserving integer keys, so ties at the k-th value are kept exactly like torch.topk +
+// `scores < kth` does.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PL_THREADS = 512;
+constexpr int PL_MAX_CAND = 1024;
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order == ascending uint order
+}
+
+__global__ void __launch_bounds__(PL_THREADS)
+process_logits_kernel(const dtts_logits_params p) {
+  extern __shared__ float sh[];          // [vocab] scores
+  __shared__ uint32_t bitmap[512];       // vocab <= 16384
+  __shared__ uint32_t hist[256];
+  __shared__ float red[40];
+  __shared__ int redi[40];
+  __shared__ uint32_t sel_prefix, sel_remaining;
+  __shared__ float cand_v[PL_MAX_CAND];
+  __shared__ int cand_i[PL_MAX_CAND];
+  __shared__ int n_cand;
+  __shared__ int n_keep;
+  __shared__ float z_keep;
+  const int row = blockIdx.x, tid = threadIdx.x, V = p.vocab;
+  const float* lg = p.logits + (long)row * p.ldl;
+  for (int i = tid; i < V; i += PL_THREADS) sh[i] = lg[i];
+  for (int i = tid; i < 512; i += PL_THREADS) bitmap[i] = 0;
+  __syncthreads();
+  // repetition penalty: every distinct id of the history is penalised once (gather/scatter semantics)
+  const int n_ids = p.n_ids + (p.step_dev ? *p.step_dev : 0);
+  const int64_t* ids = p.ids + (long)row * p.ld_ids;
+  for (int i = tid; i < n_ids; i += PL_THREADS) {
+    const int id = (int)ids[i];
+    if (id < 0 || id >= V) continue;
+    const uint32_t bit = 1u << (id & 31);
+    const uint32_t old = atomicOr(&bitmap[id >> 5], bit);
+    if (!(old & bit)) {
+      const float s = sh[id];
+      sh[id] = s < 0.f ? s * p.penalty : s / p.penalty;
+    }
+  }
+  __syncthreads();
+  if (p.suppress_token >= 0 && p.suppress_token < V && tid == 0) sh[p.suppress_token] = -INFINITY;
+  __syncthreads();
+
+  if (!p.do_sample) {
+    // argmax, lowest index on ties
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += PL_THREADS) {
+      const float s = sh[i];
+      if (s > bv || (s == bv && i < bi)) { bv = s; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red[tid >> 5] = bv; redi[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < PL_THREADS / 32; ++w)
+        if (red[w] > bv || (red[w] == bv && redi[w] < bi)) { bv = red[w]; bi = redi[w]; }
+      p.argmax[row] = bi;
+    }
+    return;
+  }
+
+  // temperature
+  for (int i = tid; i < V; i += PL_THREADS) sh[i] = sh[i] / p.temperature;
+  __syncthreads();
+  // exact k-th largest via radix select over 4 x 8 bits
+  const int k = p.top_k < V ? p.top_k : V;
+  if (tid == 0) { sel_prefix = 0; sel_remaining = (uint32_t)k; n_cand = 0; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += PL_THREADS) hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = sel_prefix;
+    const uint32_t mask_hi = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < V; i += PL_THREADS) {
+      const uint32_t key = f2key(sh[i]);
+      if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t rem = sel_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= rem) break;
+        rem -= hist[b];
+      }
+      sel_prefix = prefix | ((uint32_t)b << shift);
+      sel_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const uint32_t kth_key = sel_prefix;
+  // candidates: everything >= kth value (ties kept)
+  for (int i = tid; i < V; i += PL_THREADS) {
+    const float s = sh[i];
+    if (f2key(s) >= kth_key && s > -INFINITY) {
+      const int slot = atomicAdd(&n_cand, 1);
+      if (slot < PL_MAX_CAND) { cand_v[slot] = s; cand_i[slot] = i; }
+    }
+  }
+  __syncthreads();
+  const int nc = n_cand < PL_MAX_CAND ? n_cand : PL_MAX_CAND;
+  // sort candidates descending by (value, then index ascending) -- bitonic over next pow2
+  int np2 = 1;
+  while (np2 < nc) np2 <<= 1;
+  for (int i = nc + tid; i < np2; i += PL_THREADS) { cand_v[i] = -INFINITY; cand_i[i] = 0x7fffffff; }
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < np2 / 2; t += PL_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const float a = cand_v[lo], b = cand_v[hi];
+        const int ai = cand_i[lo], bi = cand_i[hi];
+        const bool a_first = (a > b) || (a == b && ai < bi);  // a should precede b in descending order
+        if (desc ? !a_first : a_first) {
+          cand_v[lo] = b; cand_v[hi] = a; cand_i[lo] = bi; cand_i[hi] = ai;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // top-p on the sorted candidates (one thread; nc ~ 50): HF sorts ascending, softmax, cumsum,
+  // removes cum <= 1 - top_p, always keeps the largest.
+  if (tid == 0) {
+    const float mx = cand_v[0];
+    float Z = 0.f;
+    for (int i = nc - 1; i >= 0; --i) Z += expf(cand_v[i] - mx);   // ascending accumulation
+    float cum = 0.f;
+    int keep = nc;   // keep candidates [0, keep)
+    for (int i = nc - 1; i >= 1; --i) {
+      cum += expf(cand_v[i] - mx) / Z;
+      if (cum <= 1.0f - p.top_p) keep = i; else break;
+    }
+    float Zk = 0.f;
+    for (int i = keep - 1; i >= 0; --i) Zk += expf(cand_v[i] - mx);
+    n_keep = keep;
+    z_keep = Zk;
+  }
+  __syncthreads();
+  float* pr = p.probs + (long)row * p.ldp;
+  for (int i = tid; i < V; i += PL_THREADS) pr[i] = 0.f;
+  __syncthreads();
+  const float mx = cand_v[0];
+  for (int i = tid; i < n_keep; i += PL_THREADS) pr[cand_i[i]] = expf(cand_v[i] - mx) / z_keep;
+}
+
+__global__ void __launch_bounds__(256)
+append_token_kernel(const dtts_append_params p) {
+  const int row = blockIdx.x;
+  const int step = p.step_dev ? *p.step_dev : 0;
+  __shared__ int64_t tok_s;
+  if (threadIdx.x == 0) {
+    int64_t tok = p.next[row];
+    const int unf = p.unfinished[row];
+    if (!unf) tok = p.stop_token;
+    p.ids[(long)row * p.ld_ids + p.n_ids + step] = tok;
+    const int still = unf && (tok != p.stop_token);
+    p.unfinished[row] = still;
+    if (still && p.n_unfinished) atomicAdd(p.n_unfinished, 1);
+    if (p.kv_row) p.kv_row[row] = row * p.kv_stride + p.kv_pos0 + step;
+    if (p.kv_len) p.kv_len[row] = p.kv_pos0 + step + 1;
+    tok_s = tok;
+  }
+  __syncthreads();
+  const int64_t tok = tok_s;
+  if (p.x_out) {
+    const float* te = p.tok_emb + tok * p.dim;
+    const float* pe = p.pos_emb + (long)(p.pos + step) * p.dim;
+    float* xo = p.x_out + (long)row * p.ldx;
+    for (int d = threadIdx.x; d < p.dim; d += blockDim.x) xo[d] = te[d] + pe[d];
+  }
+}
+
+__global__ void bump_step_kernel(int* step) { *step += 1; }
+
+}  // namespace
+
+extern "C" int dtts_process_logits(const dtts_logits_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->logits && p->ids, "process_logits: null argument");
+  DTTS_REQUIRE(p->vocab > 0 && p->vocab <= 16384, "process_logits: vocab out of range");
+  DTTS_REQUIRE(p->do_sample ? (p->probs != nullptr) : (p->argmax != nullptr), "process_logits: missing output");
+  DTTS_REQUIRE(!p->do_sample || (p->temperature > 0.f && p->top_k > 0 && p->top_k <= 512), "process_logits: bad sampling params");
+  if (p->n_rows <= 0) return 0;
+  process_logits_kernel<<<p->n_rows, PL_THREADS, p->vocab * sizeof(float), (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("process_logits");
+  return 0;
+}
+
+extern "C" int dtts_append_token(const dtts_append_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->next && p->ids && p->unfinished, "append_token: null argument");
+  DTTS_REQUIRE(!p->x_out || (p->tok_emb && p->pos_emb), "append_token: missing embedding tables");
+  if (p->n_rows <= 0) return 0;
+  append_token_kernel<<<p->n_rows, 256, 0, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("append_token");
+  if (p->step_dev) {
+    bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->step_dev);
+    DTTS_CHECK_LAUNCH("bump_step");
+  }
+  return 0;
+}

@@ -1,0 +1,222 @@
+/* dtts.h -- C ABI of the B200-native kernels behind detail_tts's synthesis hot path.
+ *
+ * Boundary: the reference (adelacvg/detail_tts) has no FFI; its hot path is plain PyTorch module
+ * calls.  A maintainer swaps those module bodies for calls into this
+ * library (ctypes stubs in INTEGRATION.md).  Every entry point takes DEVICE pointers owned by the
+ * caller (torch tensors' data_ptr()), launches asynchronously on the given cudaStream_t and never
+ * allocates device memory or synchronises.  Return 0 = ok, negative = error (dtts_last_error()).
+ *
+ * Activation layout ("rows"): channels-last [M, C] row-major with leading dimension ld (elements).
+ * Utterance b owns rows [utt_off[b], utt_off[b]+utt_len[b]); rows between utterances are zero
+ * separator rows (row_utt[m] == -1) that implement the reference's per-conv zero padding.
+ *
+ * Each function cites the reference code it replaces (file:line under /root/reference).
+ */
+#ifndef DTTS_H
+#define DTTS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTTS_ABI_VERSION 1
+
+/* activations usable in GEMM epilogues / elementwise kernels */
+enum {
+  DTTS_ACT_NONE = 0,
+  DTTS_ACT_GELU_NEW = 1,   /* HF gelu_new, transformers modeling_gpt2.py MLP */
+  DTTS_ACT_RELU = 2,       /* vqvae/modules/attentions.py:343 */
+  DTTS_ACT_SILU = 3,       /* vqvae/diff_model.py:83,96,163 */
+  DTTS_ACT_MISH = 4,       /* vqvae/modules/modules.py:496-501 */
+  DTTS_ACT_LRELU = 5,      /* vqvae/model_24k.py:275,284; modules.py:317,320 (slope in act_param) */
+  DTTS_ACT_TANH = 6,       /* vqvae/model_24k.py:286 */
+  /* pair activations: output column j is f(v[2j], v[2j+1]); N must be even, Nout = N/2.
+     Weights are packed with the two halves of the reference's channel split interleaved. */
+  DTTS_ACT_PAIR_TANH_SIGMOID = 16, /* fused_add_tanh_sigmoid_multiply, modules.py:15-22 */
+  DTTS_ACT_PAIR_GLU = 17           /* Conv1dGLU x1*sigmoid(x2), modules.py:518-520 */
+};
+
+typedef struct {
+  const void* A;        /* [M, K] fp16 (tc) or fp32 (simt), row-major, lda elements */
+  const void* W;        /* [taps*N, K] same dtype as A, tap-major, ldw elements */
+  int M, N, K, lda, ldw;
+  int taps;             /* number of row taps (conv kernel size); 1 = plain GEMM */
+  int tap_shift0;       /* row shift of tap 0 (e.g. -pad*dilation) */
+  int tap_stride;       /* row shift increment per tap (dilation) */
+  const float* bias;      /* [N] or NULL */
+  const float* bias_utt;  /* [n_utt, N] per-utterance bias or NULL (needs row_utt) */
+  const int* row_utt;     /* [M]: utterance id, or -1 => row is a separator (not stored); NULL = all valid */
+  const int* out_row_map; /* [M]: output/residual row index for A row m; NULL = identity */
+  const float* res;       /* fp32 residual [*, Nout], ldr; added after the activation; NULL = none */
+  float* out_f32;         /* fp32 output [*, Nout], ldo32; NULL = none */
+  void* out_f16;          /* fp16 output [*, Nout], ldo16; NULL = none */
+  int ldr, ldo32, ldo16;
+  int act;                /* DTTS_ACT_* applied to acc+bias */
+  int act16;              /* extra activation applied only to the fp16 copy (next GEMM's operand) */
+  float act_param, act16_param;
+  float alpha;            /* out = alpha*(act(acc+bias)+res) (+ out_old if accumulate) */
+  int accumulate;
+} dtts_gemm_params;
+
+/* D = epilogue(sum_taps A[m+shift_t,:] . W_t[n,:]) on tcgen05 tensor cores (fp16 operands, fp32
+ * accumulation in TMEM, TMA-staged operands).  Replaces every dense contraction on the path:
+ * nn.Conv1d / nn.Linear / ConvTranspose1d in vqvae/diff_model.py:81-99,160-209,
+ * vqvae/utils/diff_util.py:199-203, vqvae/model_24k.py:236-267, vqvae/modules/modules.py:178-200,
+ * 243-312, vqvae/modules/attentions.py:183-186,330-331, HF Conv1D in GPT2Block. */
+int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream);
+/* Same contract in exact fp32 FMA arithmetic on CUDA cores (token-exact GPT path, small shapes). */
+int dtts_gemm_f32(const dtts_gemm_params* p, void* stream);
+
+typedef struct {
+  const void* x; int x_is_f16; int ldx;   /* [M, C] */
+  int C, groups, n_utt;
+  int max_len;                             /* longest utterance (sizes the smem cache); 0 = unknown */
+  const int* utt_off; const int* utt_len;  /* [n_utt] */
+  const float* gamma; const float* beta;   /* [C] */
+  const float* film_scale; const float* film_shift; int ld_film;  /* [n_utt(or n_film), C] or NULL: y*(1+s)+b */
+  const int* film_idx;                     /* [n_utt] row of film_* used by utterance b; NULL = b */
+  int act;                                  /* DTTS_ACT_NONE or DTTS_ACT_SILU */
+  float eps;
+  float* out_f32; int ldo32; void* out_f16; int ldo16;
+} dtts_groupnorm_params;
+/* GroupNorm32 (fp32 statistics over channels-in-group x frames of ONE utterance) + optional
+ * timestep FiLM + SiLU: vqvae/utils/diff_util.py:113-133, vqvae/diff_model.py:107,113-115,242. */
+int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream);
+
+typedef struct {
+  const float* x; int ldx; int M, C;
+  const float* gamma; const float* beta; float eps;
+  const float* res; int ldr;      /* optional: normalises (x + res) */
+  float* out_f32; int ldo32; void* out_f16; int ldo16;
+} dtts_layernorm_params;
+/* LayerNorm over channels of each row: GPT2Block ln_1/ln_2/ln_f, gpt/model.py:322 final_norm,
+ * vqvae/modules/modules.py:36-48 (channel LayerNorm in enc_p). */
+int dtts_layernorm(const dtts_layernorm_params* p, void* stream);
+
+enum { DTTS_ATTN_BIAS_NONE = 0, DTTS_ATTN_BIAS_RELPOS_TABLE = 1, DTTS_ATTN_BIAS_WINDOW_REL = 2 };
+typedef struct {
+  const void* q; const void* k; const void* v;  /* element (row r, head h, dim d) at ptr[r*ld + h*head_stride + d] */
+  int is_f16; int ldq, ldk, ldv; int head_stride_q, head_stride_k, head_stride_v;
+  int n_utt, n_heads, head_dim;
+  const int* q_off; const int* q_len;    /* query rows of utterance b */
+  const int* k_off; const int* k_len;    /* key rows of utterance b */
+  int max_q_len, max_k_len;
+  int causal;                 /* key j visible to query i iff j <= i + causal_offset[b] */
+  const int* causal_offset;   /* [n_utt] or NULL (0) */
+  float scale;                /* multiplies q.k */
+  int bias_mode;
+  const float* bias_table; int bias_half;   /* RELPOS_TABLE: [n_heads, 2*bias_half+1] indexed clamp(j-i)+bias_half */
+  const float* rel_k; const float* rel_v; int window;  /* WINDOW_REL: [2*window+1, head_dim] shared over heads */
+  float* out_f32; int ldo32; void* out_f16; int ldo16;  /* [rows, n_heads*head_dim] head-major */
+} dtts_attention_params;
+/* softmax(scale*q.k + bias) v in exact fp32 on CUDA cores, one query per CTA.  Covers the small
+ * attentions: GPT-2 causal attention incl. KV-cache decode (modeling_gpt2.py:54-72),
+ * MelStyleEncoder (modules.py:565-639), enc_p windowed rel-pos attention (attentions.py:198-239),
+ * contextual_embedder / latent_conditioner (diff_util.py:145-169). */
+int dtts_attention_f32(const dtts_attention_params* p, void* stream);
+/* Flash-style tensor-core attention (fp16 operands, fp32 online softmax) for the diffusion
+ * AttentionBlock hot loop: vqvae/utils/diff_util.py:145-169 + xtransformers.py:177-186.
+ * Requires is_f16, head_dim 48, bias_mode NONE or RELPOS_TABLE, non-causal. */
+int dtts_attention_f16_flash(const dtts_attention_params* p, void* stream);
+
+typedef struct {
+  const float* logits; int ldl; int n_rows, vocab;
+  const int64_t* ids; int ld_ids; int n_ids;     /* history incl. fake prefix (repetition penalty set) */
+  const int* step_dev;                           /* optional device scalar added to n_ids (CUDA-graph replay) */
+  float penalty, temperature, top_p; int top_k;
+  int do_sample; int suppress_token;             /* -1 = none */
+  float* probs; int ldp;                         /* do_sample: dense probabilities [n_rows, vocab] */
+  int64_t* argmax;                               /* greedy: [n_rows] */
+} dtts_logits_params;
+/* HF processor chain RepetitionPenalty -> Temperature -> TopK -> TopP -> softmax (or argmax):
+ * transformers generation/logits_process.py:298,407-410,522-532,582-585 as driven by
+ * vqvae/model_24k.py:782-792 / gpt/model.py:540-544. */
+int dtts_process_logits(const dtts_logits_params* p, void* stream);
+
+typedef struct {
+  int n_rows;
+  const int64_t* next; int64_t* ids; int ld_ids; int n_ids;  /* ids[:, n_ids] = next (or stop if finished) */
+  int* step_dev;                 /* optional device scalar: added to n_ids and pos, incremented by the kernel */
+  int* unfinished; int* n_unfinished; int64_t stop_token;   /* n_unfinished: rows still running after this token */
+  const float* tok_emb; const float* pos_emb; int pos; int dim;   /* next-step embedding row */
+  float* x_out; int ldx;
+  int* kv_row; int kv_stride;    /* optional [n_rows]: kv_row[b] = b*kv_stride + kv_pos0 + step (next KV/out row) */
+  int kv_pos0; int* kv_len;      /* optional [n_rows]: kv_len[b] = kv_pos0 + step + 1 (keys visible next step) */
+} dtts_append_params;
+/* HF _sample bookkeeping (generation/utils.py:2797-2805) + next-token embedding
+ * mel_embedding[id] + mel_pos_embedding[pos] (gpt/model.py:145-148). */
+int dtts_append_token(const dtts_append_params* p, void* stream);
+
+typedef struct {
+  int M, C;                     /* rows, channels (128) */
+  float* x; int ldx;            /* in/out fp32 state */
+  const float* out_c; const float* out_u; int ldo;   /* [M, 2C] model outputs (eps | var) */
+  const float* noise; int ldn;  /* [M, C] */
+  float sqrt_recip, sqrt_recipm1, min_log, max_log, coef1, coef2, cfk, nonzero;
+  void* x_f16; int ldx16;       /* optional fp16 copy of the new state */
+} dtts_pstep_params;
+/* One ancestral DDPM update with classifier-free guidance and learned-range variance:
+ * vqvae/utils/diffusion.py:317-386,472-485. */
+int dtts_p_sample_step(const dtts_pstep_params* p, void* stream);
+
+/* elementwise / layout helpers (all on rows layout unless stated) */
+typedef struct {
+  const float* src; int B, C, T; const int* utt_off; const int* utt_len;  /* src [B, C, T] (reference layout) */
+  float* dst_f32; int ld32; void* dst_f16; int ld16; float scale, shift;
+} dtts_bct2rows_params;
+int dtts_bct_to_rows(const dtts_bct2rows_params* p, void* stream);     /* [B,C,T] -> rows (x*scale+shift) */
+typedef struct {
+  const float* src; int ld; int B, C, T; const int* utt_off; const int* utt_len;
+  float* dst; float scale, shift;                                       /* dst [B, C, T], zero beyond utt_len */
+} dtts_rows2bct_params;
+int dtts_rows_to_bct(const dtts_rows2bct_params* p, void* stream);
+typedef struct {
+  const float* x; int ldx; int M, C; int act; float act_param; float scale;
+  float* out_f32; int ldo32; void* out_f16; int ldo16; const int* row_utt;
+} dtts_eltwise_params;
+int dtts_eltwise(const dtts_eltwise_params* p, void* stream);          /* out = act(x)*scale, masked rows -> 0 */
+typedef struct {
+  const int64_t* ids; int n; const float* table; int dim; const float* pos_table; const int* pos; /* pos[n] or NULL */
+  float* out; int ldo;
+} dtts_embed_params;
+int dtts_embed(const dtts_embed_params* p, void* stream);              /* gpt/model.py:134-136,517-519 */
+typedef struct {
+  const float* x; int ldx; int C; int n_utt; const int* utt_off; const int* utt_len; int repeat;
+  float* out; int ldo; const int* out_off;
+} dtts_repeat_rows_params;
+int dtts_repeat_rows(const dtts_repeat_rows_params* p, void* stream);  /* F.interpolate nearest xN, diff_model.py:252 */
+typedef struct {
+  const float* x; int ldx; int C; int n_utt; const int* utt_off; const int* utt_len; float* out; int ldo;
+} dtts_mean_rows_params;
+int dtts_mean_rows(const dtts_mean_rows_params* p, void* stream);      /* masked temporal mean, modules.py:686-694; diff_model.py:228 */
+typedef struct {
+  const float* t; int n; int dim; float* out; int ldo; void* out_f16; int ldo16;
+} dtts_tsemb_params;
+int dtts_timestep_embedding(const dtts_tsemb_params* p, void* stream); /* vqvae/diff_model.py:20-38 */
+typedef struct {
+  float* x; int ldx; int M, half;            /* x [M, 2*half] */
+  const float* m; int ldm; const int* row_utt;
+  void* x0_f16; int ld16;                    /* optional: fp16 copy of x[:, :half] after the update (next pre-conv operand) */
+  int flip_after;                            /* then flip channels in place (Flip, modules.py:393-400) */
+} dtts_couple_params;
+/* x1 = (x1 - m)*mask (m may be NULL = skip), modules.py:472-474, then optional Flip, then fp16 x0 copy */
+int dtts_flow_couple(const dtts_couple_params* p, void* stream);
+typedef struct {
+  const float* m; const float* logs; int ld; const float* noise; int ldn; int M, C; float noise_scale;
+  float* out; int ldo; const int* row_utt;
+} dtts_zp_params;
+int dtts_sample_zp(const dtts_zp_params* p, void* stream);             /* vqvae/model_24k.py:860 */
+typedef struct { int* row_utt; int M; int n_utt; const int* utt_off; const int* utt_len; } dtts_rowutt_params;
+int dtts_fill_row_utt(const dtts_rowutt_params* p, void* stream);
+
+/* library info */
+int dtts_abi_version(void);
+const char* dtts_last_error(void);
+int dtts_sizeof(const char* struct_name);   /* sizeof(<struct>) for the binding's layout self-check */
+int dtts_kernel_launches(void);             /* kernels launched by this library since load (bench gpu_launches) */
+int dtts_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
