@@ -199,7 +199,7 @@ flash48_kernel(const dtts_attention_params p) {
     const int i = qi0 + r * 8;
     if (i >= qlen) continue;
     const float inv = 1.0f / l_run[r];
-    const long orow = (long)p.q_off[b] + i;
+    const long orow = (long)(p.o_off ? p.o_off[b] : p.q_off[b]) + i;
 #pragma unroll
     for (int dt = 0; dt < 6; ++dt) {
       const int d = h * HD + dt * 8 + tig * 2;

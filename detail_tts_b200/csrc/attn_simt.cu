@@ -85,7 +85,7 @@ attention_simt_kernel(const dtts_attention_params p) {
     float t = 0.f;
     for (int q_ = 0; q_ < JP; ++q_) t += part[q_ * hd + threadIdx.x];
     t *= inv;
-    const long orow = p.q_off[b] + i;
+    const long orow = (p.o_off ? p.o_off[b] : p.q_off[b]) + i;
     if (p.out_f32) p.out_f32[orow * p.ldo32 + h * hd + threadIdx.x] = t;
     if (p.out_f16) ((__half*)p.out_f16)[orow * p.ldo16 + h * hd + threadIdx.x] = __float2half_rn(t);
   }

@@ -102,7 +102,7 @@ embed_kernel(const dtts_embed_params p) {
   const long id = p.ids[i];
   const float* te = p.table + id * p.dim;
   const float* pe = p.pos_table ? p.pos_table + (long)(p.pos ? p.pos[i] : i) * p.dim : nullptr;
-  float* o = p.out + (long)i * p.ldo;
+  float* o = p.out + (long)(p.dst_row ? p.dst_row[i] : i) * p.ldo;
   for (int d = threadIdx.x; d < p.dim; d += blockDim.x) o[d] = te[d] + (pe ? pe[d] : 0.f);
 }
 
@@ -146,7 +146,7 @@ tsemb_kernel(const dtts_tsemb_params p) {
   const int i = blockIdx.x, half = p.dim / 2;
   const float t = p.t[i];
   for (int k = threadIdx.x; k < half; k += blockDim.x) {
-    const float f = expf(-9.210340371976184f * (float)k / (float)half);
+    const float f = (float)exp(-9.210340371976184 * (double)k / (double)half);
     const float a = t * f;
     const float c = cosf(a), s = sinf(a);
     if (p.out) { p.out[(long)i * p.ldo + k] = c; p.out[(long)i * p.ldo + half + k] = s; }

@@ -111,10 +111,12 @@ constexpr int LN_MAXE = 32;  // C <= 1024
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const float* __restrict__ res, int ldr,
-                 float* __restrict__ out32, int ldo32, __half* __restrict__ out16, int ldo16) {
+                 float* __restrict__ out32, int ldo32, __half* __restrict__ out16, int ldo16,
+                 const int* __restrict__ row_utt) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
+  if (row_utt && row_utt[row] < 0) return;
   float v[LN_MAXE];
   float s = 0.f;
 #pragma unroll
@@ -192,7 +194,7 @@ extern "C" int dtts_layernorm(const dtts_layernorm_params* p, void* stream) {
   if (p->M <= 0) return 0;
   const int rows_per_cta = 8;
   layernorm_kernel<<<ceil_div(p->M, rows_per_cta), rows_per_cta * 32, 0, (cudaStream_t)stream>>>(
-      p->x, p->ldx, p->M, p->C, p->gamma, p->beta, p->eps, p->res, p->ldr, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
+      p->x, p->ldx, p->M, p->C, p->gamma, p->beta, p->eps, p->res, p->ldr, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16, p->row_utt);
   DTTS_CHECK_LAUNCH("layernorm");
   return 0;
 }

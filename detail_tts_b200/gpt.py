@@ -1,0 +1,396 @@
+"""GPT autoregressive code-token decoder of the synthesis path, on the dtts kernels.
+
+Mirrors the reference's call surface (gpt/model.py):
+  UnifiedVoice.inference_speech_tortoise(speech_conditioning_latent, cond_lengths, text_inputs, ...)
+      gpt/model.py:514-545  (+ alias inference_speech, gpt/model_deprect.py:528)
+  UnifiedVoice.forward(..., return_latent=True)              gpt/model.py:429-491
+  MelStyleEncoder.forward                                     vqvae/modules/modules.py:696-720
+What differs by design: the reference builds the trunk with kv_cache=False (vqvae/model_24k.py:602) and
+re-runs the whole prefix every token through HF generate(); here a prefill writes a KV arena and every
+token is ONE decode step over B rows (LN -> QKV GEMM -> cached attention -> proj -> LN -> FFN),
+followed on-device by the HF processor chain (sampling.cu) with no per-token host sync.
+Numerics: fp32 operands/accumulation by default (token-exact sampling needs fp32-class logits,
+SURVEY.md section 7); `dtype=torch.float16` selects the tcgen05 path.
+"""
+import math
+
+import torch
+
+from . import ops, pack
+from .ops import RowsLayout
+
+START_TEXT, STOP_TEXT = 255, 0
+START_MEL, STOP_MEL = 8192, 8193
+N_LAYERS, N_HEADS, D_MODEL, HEAD_DIM = 10, 16, 768, 48
+VOCAB = 8194
+
+
+def _i32(x, device):
+    return torch.tensor(x, dtype=torch.int32, device=device)
+
+
+class MelStyleEncoder:
+    """vqvae/modules/modules.py:642-720 on rows layout.  `__call__(x [B,n_mel,T], mask|lengths)` ->
+    [B, out_dim, 1] like the reference; varlen batches are evaluated per utterance (each utterance
+    sees zero padding at its own ends, i.e. exactly the reference at B=1)."""
+
+    def __init__(self, W, prefix, dtype, device):
+        self.dtype, self.device = dtype, device
+        g = lambda k: W[prefix + k]  # noqa: E731
+        self.n_mel = g("spectral.0.fc.weight").shape[1]
+        self.hid = g("spectral.0.fc.weight").shape[0]
+        self.out_dim = g("fc.fc.weight").shape[0]
+        pl = lambda w, b: pack.pack_linear(g(w), g(b), dtype, device)  # noqa: E731
+        self.sp0 = pl("spectral.0.fc.weight", "spectral.0.fc.bias")
+        self.sp1 = pl("spectral.3.fc.weight", "spectral.3.fc.bias")
+        self.glu = []
+        for i in range(2):
+            w, b, _ = pack.interleave_halves(g(f"temporal.{i}.conv1.conv.weight"), g(f"temporal.{i}.conv1.conv.bias"))
+            self.glu.append(pack.pack_conv1d(w, b, dtype, device, padding=(w.shape[2] - 1) // 2))
+        wqkv = torch.cat([g("slf_attn.w_qs.weight"), g("slf_attn.w_ks.weight"), g("slf_attn.w_vs.weight")], 0)
+        bqkv = torch.cat([g("slf_attn.w_qs.bias"), g("slf_attn.w_ks.bias"), g("slf_attn.w_vs.bias")], 0)
+        self.qkv = pack.pack_linear(wqkv, bqkv, dtype, device)
+        self.afc = pl("slf_attn.fc.weight", "slf_attn.fc.bias")
+        self.fc = pl("fc.fc.weight", "fc.fc.bias")
+
+    def _o(self, t):
+        return {"out16": t} if self.dtype == torch.float16 else {"out32": t}
+
+    def __call__(self, x, mask=None, lengths=None):
+        B, C, T = x.shape
+        if lengths is None:
+            lengths = [T] * B if mask is None else mask.reshape(B, -1).sum(1).long().tolist()
+        return self.forward_rows(x, [int(v) for v in lengths]).unsqueeze(-1)
+
+    def forward_rows(self, x, lengths):
+        dev, dt, hid = self.device, self.dtype, self.hid
+        lay = RowsLayout(lengths, 2, dev)
+        M, ru = lay.M, lay.row_utt
+        z = lambda c, d=dt: torch.zeros(M, c, dtype=d, device=dev)  # noqa: E731
+        x0 = z(self.n_mel)
+        ops.bct_to_rows(x.contiguous().float(), lay, **({"dst16": x0} if dt == torch.float16 else {"dst32": x0}))
+        h1 = z(hid)
+        ops.gemm(x0, self.sp0, act=ops.ACT_MISH, row_utt=ru, **self._o(h1))
+        h32, hdt = z(hid, torch.float32), None
+        if dt == torch.float16:
+            hdt = z(hid)
+            ops.gemm(h1, self.sp1, act=ops.ACT_MISH, row_utt=ru, out32=h32, out16=hdt)
+        else:
+            ops.gemm(h1, self.sp1, act=ops.ACT_MISH, row_utt=ru, out32=h32)
+            hdt = h32
+        for pw in self.glu:
+            n32 = z(hid, torch.float32)
+            if dt == torch.float16:
+                ndt = z(hid)
+                ops.gemm(hdt, pw, act=ops.ACT_PAIR_GLU, res=h32, row_utt=ru, out32=n32, out16=ndt)
+            else:
+                ops.gemm(hdt, pw, act=ops.ACT_PAIR_GLU, res=h32, row_utt=ru, out32=n32)
+                ndt = n32
+            h32, hdt = n32, ndt
+        qkv = z(3 * hid)
+        ops.gemm(hdt, self.qkv, row_utt=ru, **self._o(qkv))
+        a = z(hid)
+        hd = hid // 2
+        ops.attention(qkv, qkv[:, hid:], qkv[:, 2 * hid:], 2, hd, lay.off, lay.len, lay.off, lay.len, lay.max_len,
+                      lay.max_len, 1.0 / math.sqrt(hid), **self._o(a))
+        x2 = z(hid)
+        ops.gemm(a, self.afc, res=h32, row_utt=ru, **self._o(x2))
+        y = z(self.out_dim, torch.float32)
+        ops.gemm(x2, self.fc, row_utt=ru, out32=y)
+        out = torch.empty(lay.n, self.out_dim, dtype=torch.float32, device=dev)
+        ops.mean_rows(y, lay, out, self.out_dim)
+        return out
+
+
+class _Trunk:
+    """HF GPT2Model weights (wpe nulled: gpt/model.py:12-13,233-234) in GEMM form."""
+
+    def __init__(self, W, dtype, device, p="gpt.gpt."):
+        f32 = lambda k: W[k].to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        self.layers = []
+        for l in range(N_LAYERS):
+            q = p + f"h.{l}."
+            self.layers.append(dict(
+                ln1=(f32(q + "ln_1.weight"), f32(q + "ln_1.bias")),
+                ln2=(f32(q + "ln_2.weight"), f32(q + "ln_2.bias")),
+                attn=pack.pack_hf_conv1d(W[q + "attn.c_attn.weight"], W[q + "attn.c_attn.bias"], dtype, device),
+                proj=pack.pack_hf_conv1d(W[q + "attn.c_proj.weight"], W[q + "attn.c_proj.bias"], dtype, device),
+                fc=pack.pack_hf_conv1d(W[q + "mlp.c_fc.weight"], W[q + "mlp.c_fc.bias"], dtype, device),
+                out=pack.pack_hf_conv1d(W[q + "mlp.c_proj.weight"], W[q + "mlp.c_proj.bias"], dtype, device)))
+        self.ln_f = (f32(p + "ln_f.weight"), f32(p + "ln_f.bias"))
+
+
+class UnifiedVoice:
+    def __init__(self, W, device="cuda", dtype=torch.float32):
+        self.device, self.dtype = torch.device(device), dtype
+        dev = self.device
+        f32 = lambda k: W[k].to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self.trunk = _Trunk(W, dtype, dev)
+        self.final_norm = (f32("gpt.final_norm.weight"), f32("gpt.final_norm.bias"))
+        self.mel_head = pack.pack_linear(W["gpt.mel_head.weight"], W["gpt.mel_head.bias"], dtype, dev)
+        self.mel_embedding = f32("gpt.mel_embedding.weight")
+        self.mel_pos = f32("gpt.mel_pos_embedding.emb.weight")
+        self.text_embedding = f32("gpt.text_embedding.weight")
+        self.text_pos = f32("gpt.text_pos_embedding.emb.weight")
+        self.conditioning_encoder = MelStyleEncoder(W, "gpt.conditioning_encoder.", dtype, dev)
+        self.max_mel_positions = self.mel_pos.shape[0]
+        self.last_latents = None
+        self.last_lengths = None
+
+    # ------------------------------------------------------------------------------------------
+    def _o(self, t):
+        return {"out16": t} if self.dtype == torch.float16 else {"out32": t}
+
+    def _text_lengths(self, text_inputs, text_lengths):
+        B, L = text_inputs.shape
+        if text_lengths is None:
+            return [L] * B
+        return [int(v) for v in text_lengths]
+
+    def _build_sequences(self, cond, text_inputs, tl, mel_ids=None, mel_lens=None):
+        """Embedding rows for [cond, <start_text>, text, <stop_text>, mel tokens...] per utterance in a
+        compact layout.  Returns (x32 [M,768], seq_off list, seq_len list, P list)."""
+        dev = self.device
+        B = text_inputs.shape[0]
+        P = [l + 3 for l in tl]                      # cond + start + L + stop
+        n_mel = [0] * B if mel_ids is None else [int(v) for v in mel_lens]
+        seq_len = [P[b] + n_mel[b] for b in range(B)]
+        seq_off, o = [], 0
+        for n in seq_len:
+            seq_off.append(o)
+            o += n
+        x = torch.empty(o, D_MODEL, dtype=torch.float32, device=dev)
+        # cond rows
+        ops.embed(torch.arange(B, device=dev), cond, x, dst_row=_i32(seq_off, dev))
+        # text rows
+        ids, pos, dst = [], [], []
+        tcpu = text_inputs.detach().to("cpu", torch.long)
+        for b in range(B):
+            row = [START_TEXT] + tcpu[b, :tl[b]].tolist() + [STOP_TEXT]
+            ids += row
+            pos += list(range(len(row)))
+            dst += [seq_off[b] + 1 + i for i in range(len(row))]
+        ops.embed(torch.tensor(ids, dtype=torch.long, device=dev), self.text_embedding, x, pos_table=self.text_pos,
+                  pos=_i32(pos, dev), dst_row=_i32(dst, dev))
+        if mel_ids is not None:
+            ids, pos, dst = [], [], []
+            mcpu = mel_ids.detach().to("cpu", torch.long)
+            for b in range(B):
+                row = mcpu[b, :n_mel[b]].tolist()
+                ids += row
+                pos += list(range(len(row)))
+                dst += [seq_off[b] + P[b] + i for i in range(len(row))]
+            ops.embed(torch.tensor(ids, dtype=torch.long, device=dev), self.mel_embedding, x, pos_table=self.mel_pos,
+                      pos=_i32(pos, dev), dst_row=_i32(dst, dev))
+        return x, seq_off, seq_len, P
+
+    def _trunk_rows(self, x, seq_off, seq_len, arena=None, arena_stride=0):
+        """All positions of every sequence through the 10 blocks + ln_f (causal attention).  With
+        `arena` (list of per-layer [B*stride, 2304] buffers) the QKV rows are scattered into it so a
+        decode loop can continue from them.  x is updated in place; returns ln_f(x) fp32."""
+        dev, dt = self.device, self.dtype
+        M = x.shape[0]
+        B = len(seq_len)
+        so, sl = _i32(seq_off, dev), _i32(seq_len, dev)
+        max_len = max(seq_len)
+        row_map = None
+        if arena is not None:
+            rm = []
+            for b in range(B):
+                rm += [b * arena_stride + i for i in range(seq_len[b])]
+            row_map = _i32(rm, dev)
+            qoff = _i32([b * arena_stride for b in range(B)], dev)
+        h = torch.empty(M, D_MODEL, dtype=dt, device=dev)
+        a = torch.empty(M, D_MODEL, dtype=dt, device=dev)
+        u = torch.empty(M, 4 * D_MODEL, dtype=dt, device=dev)
+        qkv_c = None if arena is not None else torch.empty(M, 3 * D_MODEL, dtype=dt, device=dev)
+        for l, ly in enumerate(self.trunk.layers):
+            ops.layernorm(x, *ly["ln1"], **self._o(h))
+            if arena is not None:
+                qkv = arena[l]
+                ops.gemm(h, ly["attn"], out_row_map=row_map, **self._o(qkv))
+                q_off = qoff
+            else:
+                qkv = qkv_c
+                ops.gemm(h, ly["attn"], **self._o(qkv))
+                q_off = so
+            ops.attention(qkv, qkv[:, D_MODEL:], qkv[:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, q_off, sl, q_off, sl,
+                          max_len, max_len, HEAD_DIM ** -0.5, causal=True, o_off=so, **self._o(a))
+            ops.gemm(a, ly["proj"], res=x, out32=x)
+            ops.layernorm(x, *ly["ln2"], **self._o(h))
+            ops.gemm(h, ly["fc"], act=ops.ACT_GELU_NEW, **self._o(u))
+            ops.gemm(u, ly["out"], res=x, out32=x)
+        y = torch.empty(M, D_MODEL, dtype=torch.float32, device=dev)
+        ops.layernorm(x, *self.trunk.ln_f, out32=y)
+        return y
+
+    def get_conditioning(self, speech_conditioning_latent, cond_lengths):
+        """gpt/model.py:521-523 -> [B, 768]"""
+        lens = [int(v) for v in cond_lengths]
+        return self.conditioning_encoder.forward_rows(speech_conditioning_latent, lens)
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def inference_speech_tortoise(self, speech_conditioning_latent, cond_lengths, text_inputs, input_tokens=None,
+                                  num_return_sequences=1, max_generate_length=None, typical_sampling=False,
+                                  typical_mass=.9, text_lengths=None, multinomial=None, sync_every=8,
+                                  **hf_generate_kwargs):
+        """gpt/model.py:514-545.  Returns codes [B, G<=max_generate_length] (rows padded with 8193
+        after EOS), as HF generate()[:, trunc_index:] does.  Supported generate kwargs are the ones the
+        reference passes (vqvae/model_24k.py:782-792): do_sample, top_p, temperature, top_k (HF
+        default 50), repetition_penalty, length_penalty (ignored when sampling, as in HF),
+        suppress_tokens=[8193].  `multinomial(probs)->[B,1]` overrides torch.multinomial (tests)."""
+        assert input_tokens is None and num_return_sequences == 1 and not typical_sampling, \
+            "only the configuration SynthesizerTrn.infer uses is implemented"
+        kw = dict(hf_generate_kwargs)
+        do_sample = bool(kw.pop("do_sample", False))
+        top_p = float(kw.pop("top_p", 1.0))
+        temperature = float(kw.pop("temperature", 1.0))
+        top_k = int(kw.pop("top_k", 50))
+        penalty = float(kw.pop("repetition_penalty", 1.0))
+        kw.pop("length_penalty", None)
+        suppress = kw.pop("suppress_tokens", None)
+        suppress_token = -1
+        if suppress:
+            assert list(suppress) == [STOP_MEL], "only suppress_tokens=[8193] is supported"
+            suppress_token = STOP_MEL
+        if kw:
+            raise TypeError(f"unsupported generate kwargs: {sorted(kw)}")
+        dev, dt = self.device, self.dtype
+        B = text_inputs.shape[0]
+        tl = self._text_lengths(text_inputs, text_lengths)
+        G = int(max_generate_length) if max_generate_length is not None else self.max_mel_positions - 3
+        assert 1 <= G <= self.max_mel_positions - 2
+
+        cond = self.get_conditioning(speech_conditioning_latent.to(dev), cond_lengths)
+        start = torch.full((B, 1), START_MEL, dtype=torch.long, device=dev)
+        x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, start, [1] * B)
+        Pmax = max(P)
+        stride = Pmax + 1 + G                       # KV arena rows per utterance
+        arena = [torch.zeros(B * stride, 3 * D_MODEL, dtype=dt, device=dev) for _ in range(N_LAYERS)]
+        y = self._trunk_rows(x, seq_off, seq_len, arena, stride)
+
+        # --- decode state (all on device; fixed buffers so the step is a replayable Plan) ----------
+        last_rows = _i32([seq_off[b] + seq_len[b] - 1 for b in range(B)], dev)
+        ld_ids = Pmax + 1 + G + 1
+        # HF repetition penalty sees the whole row: P fake 1's, 8192, then generated ids.  Rows are
+        # right-aligned per utterance so that column n_ids0+s is generated token s for every row.
+        ids = torch.ones(B, ld_ids, dtype=torch.long, device=dev)
+        ids[:, Pmax] = START_MEL
+        n_ids0 = Pmax + 1
+        xs = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)       # decode-step residual stream
+        hn = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
+        hdt = torch.empty(B, D_MODEL, dtype=dt, device=dev)
+        adt = torch.empty(B, D_MODEL, dtype=dt, device=dev)
+        udt = torch.empty(B, 4 * D_MODEL, dtype=dt, device=dev)
+        t32 = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
+        logits = torch.empty(B, VOCAB, dtype=torch.float32, device=dev)
+        probs = torch.zeros(B, VOCAB, dtype=torch.float32, device=dev)
+        argmax = torch.zeros(B, dtype=torch.long, device=dev)
+        unfinished = torch.ones(B, dtype=torch.int32, device=dev)
+        step = torch.zeros(1, dtype=torch.int32, device=dev)
+        kv_row = torch.zeros(B, dtype=torch.int32, device=dev)
+        kv_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        k_off = _i32([b * stride for b in range(B)], dev)
+        iota = torch.arange(B, dtype=torch.int32, device=dev)
+        ones = torch.ones(B, dtype=torch.int32, device=dev)
+        # per-utterance KV position of generated token s is P_b + 1 + s; kv_row/kv_len need per-row
+        # bases, so keep them as (base + step) computed by a tiny kernel: base arrays below.
+        latents = torch.zeros(B, G + 1, D_MODEL, dtype=torch.float32, device=dev)
+
+        lib = ops._lib.lib()
+
+        def head(src_rows_x, M, first):
+            """ln_f'd hidden -> final_norm -> logits -> processed probs/argmax"""
+            ops.layernorm(src_rows_x, *self.final_norm, out32=hn, **({"out16": hdt} if dt == torch.float16 else {}))
+            ops.gemm(hdt if dt == torch.float16 else hn, self.mel_head, out32=logits)
+            lib.call("dtts_process_logits", logits=logits, ldl=VOCAB, n_rows=B, vocab=VOCAB, ids=ids, ld_ids=ld_ids,
+                     n_ids=n_ids0, step_dev=step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                     do_sample=int(do_sample), suppress_token=suppress_token, probs=probs, ldp=VOCAB, argmax=argmax)
+
+        # first token: from the prefill's last position of every utterance
+        y_last = y.index_select(0, last_rows.long())
+        head(y_last, B, True)
+        latents[:, 0].copy_(hn)
+
+        kv_base = _i32([P[b] + 1 for b in range(B)], dev)        # KV position of generated token 0
+
+        with lib.record() as plan:
+            for l, ly in enumerate(self.trunk.layers):
+                ops.layernorm(xs, *ly["ln1"], **self._o(hdt))
+                ops.gemm(hdt, ly["attn"], out_row_map=kv_row, **self._o(arena[l]))
+                ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
+                              ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, **self._o(adt))
+                ops.gemm(adt, ly["proj"], res=xs, out32=xs)
+                ops.layernorm(xs, *ly["ln2"], **self._o(hdt))
+                ops.gemm(hdt, ly["fc"], act=ops.ACT_GELU_NEW, **self._o(udt))
+                ops.gemm(udt, ly["out"], res=xs, out32=xs)
+            ops.layernorm(xs, *self.trunk.ln_f, out32=t32)
+            head(t32, B, False)
+
+        def append(nxt):
+            lib.call("dtts_append_token", n_rows=B, next=nxt, ids=ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=step,
+                     unfinished=unfinished, stop_token=STOP_MEL, tok_emb=self.mel_embedding, pos_emb=self.mel_pos,
+                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL)
+
+        n_gen = 0
+        for s in range(G):
+            if do_sample:
+                nxt = (multinomial(probs) if multinomial is not None else torch.multinomial(probs, 1)).reshape(B)
+                nxt = nxt.to(dev)
+            else:
+                nxt = argmax
+            append(nxt)                      # ids[:, n_ids0+s] = token s; xs = emb(token s) + mel_pos[s+1]; step++
+            n_gen = s + 1
+            if s + 1 >= G:
+                break
+            if (s + 1) % sync_every == 0 or B == 1:
+                if int(unfinished.sum()) == 0:
+                    break
+            # KV rows of this step: position P_b + 1 + s of utterance b
+            torch.add(kv_base, s, out=kv_len)
+            torch.add(k_off, kv_len, out=kv_row)
+            kv_len.add_(1)
+            plan.run()
+            latents[:, s + 1].copy_(hn)
+        codes = ids[:, n_ids0:n_ids0 + n_gen].clone()
+        # trim trailing all-pad columns produced between host checks
+        if n_gen > 1:
+            fin = (codes == STOP_MEL)
+            done_at = torch.where(fin.any(1), fin.float().argmax(1) + 1, torch.full((B,), n_gen, device=dev))
+            n_keep = int(done_at.max())
+            codes = codes[:, :n_keep]
+        self.last_latents = latents
+        return codes
+
+    inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, speech_conditioning_latent, cond_lengths, text_inputs, text_lengths, mel_codes, wav_lengths,
+                cond_mel_lengths=None, types=None, text_first=True, raw_mels=None, return_attentions=False,
+                return_latent=False, clip_inputs=False, mel_lengths=None):
+        """UnifiedVoice.forward(return_latent=True, clip_inputs=False) as SynthesizerTrn.infer calls it
+        (vqvae/model_24k.py:796-799): [B,T] codes -> latents [B,T,768] (double-normed hidden at mel input
+        positions 0..T-1).  `mel_lengths` (new, optional) gives per-utterance T for varlen batches; padded
+        latent rows are zero.  Only the return_latent path exists (the loss path is training)."""
+        assert return_latent, "only return_latent=True is on the synthesis path"
+        dev = self.device
+        B, Tm = mel_codes.shape
+        tl = self._text_lengths(text_inputs, None)
+        ml = [Tm] * B if mel_lengths is None else [int(v) for v in mel_lengths]
+        cond = self.get_conditioning(speech_conditioning_latent.to(dev), cond_lengths)
+        mc = mel_codes.to(dev, torch.long)
+        seqs = torch.full((B, Tm + 2), STOP_MEL, dtype=torch.long, device=dev)
+        seqs[:, 0] = START_MEL
+        for b in range(B):
+            seqs[b, 1:1 + ml[b]] = mc[b, :ml[b]]
+        x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, seqs, [m + 2 for m in ml])
+        y = self._trunk_rows(x, seq_off, seq_len)
+        yn = torch.empty_like(y)
+        ops.layernorm(y, *self.final_norm, out32=yn)
+        out = torch.zeros(B, Tm, D_MODEL, dtype=torch.float32, device=dev)
+        for b in range(B):
+            s0 = seq_off[b] + P[b]
+            out[b, :ml[b]] = yn[s0:s0 + ml[b]]
+        return out

@@ -1,0 +1,124 @@
+"""SynthesizerTrn: the container the reference's api.py calls (vqvae/model_24k.py:515-810).
+
+Keeps the reference's inference surface -- `infer`, `infer_flowvae`, attributes `gpt`, `diffusion`,
+`infer_diffuser`, `dec`, `enc_p`, `flow`, `ref_enc` -- and adds `infer_batch`, because the reference's
+`infer` hard-slices batch item 0 (model_24k.py:775-778).  Weights come from the reference's own
+checkpoint format (prepare/load_infer.py:8-34: `torch.load(path)['G' | 'model']`).
+"""
+import json
+import os
+
+import torch
+
+from . import synth
+from .diffusion import DiffusionTts, SpacedDiffusion, denormalize_torch_mel, do_spectrogram_diffusion, space_timesteps
+from .flowvae import FlowVAE
+from .gpt import STOP_MEL, UnifiedVoice
+
+
+class SynthesizerTrn:
+    def __init__(self, state_dict, device="cuda", gpt_dtype=torch.float32, diffusion_steps=50):
+        if not torch.cuda.is_available():
+            raise RuntimeError("detail_tts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        W = state_dict
+        self.gpt = UnifiedVoice(W, self.device, gpt_dtype)
+        self.diffusion = DiffusionTts(W, self.device)
+        # vqvae/model_24k.py:578-583: training diffuser (4000 steps) is not on the path; the inference one is
+        self.infer_diffuser = SpacedDiffusion(use_timesteps=space_timesteps(4000, [diffusion_steps]),
+                                              conditioning_free=True, conditioning_free_k=2.0, sampler="dpm++2m")
+        self.flowvae = FlowVAE(W, self.device)
+        self.ref_enc, self.enc_p, self.flow, self.dec = (self.flowvae.ref_enc, self.flowvae.enc_p, self.flowvae.flow,
+                                                         self.flowvae.dec)
+        self.capture_latents = True     # take the diffusion latents from the decode steps
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        assert torch.device(device).type == "cuda"
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer_batch(self, text, text_lengths, refer, refer_lengths, noise_scale=0.667, max_generate_length=600,
+                    do_sample=True, suppress_eos=False, hooks=None, trace=None):
+        """Batched SynthesizerTrn.infer: every utterance b is synthesised exactly as the reference would at
+        B=1 (own lengths, own GroupNorm statistics and attention extents).
+        text [B,Lmax] int (each row = tokens + api.py's trailing 0 pad), text_lengths [B] (counting that
+        pad), refer [B,128,Rmax] log-mel, refer_lengths [B].
+        Returns (wav [B,1,1024*Tmax] zero beyond each utterance, wav_lengths [B] in samples).
+        `hooks`: optional dict of RNG overrides {multinomial, randn, randn_like, randn_like_zp} (tests)."""
+        hooks = hooks or {}
+        dev = self.device
+        B = text.shape[0]
+        tl = [int(v) for v in text_lengths]
+        rl = [int(v) for v in refer_lengths]
+        refer = refer.to(dev, torch.float32)
+        kw = dict(do_sample=do_sample, repetition_penalty=2.0, num_return_sequences=1,
+                  max_generate_length=max_generate_length, text_lengths=tl, multinomial=hooks.get("multinomial"))
+        if do_sample:
+            kw.update(top_p=.8, temperature=.8, length_penalty=1.0)         # model_24k.py:786-791
+        if suppress_eos:
+            kw["suppress_tokens"] = [STOP_MEL]
+        codes = self.gpt.inference_speech_tortoise(refer, rl, text, **kw)
+        # model_24k.py:795: codes[:, :-1] drops the stop token (or the last token when the cap was hit)
+        G = codes.shape[1]
+        fin = codes == STOP_MEL
+        first_stop = torch.where(fin.any(1), fin.float().argmax(1), torch.full((B,), G, device=dev))
+        gen_len = torch.clamp(first_stop + 1, max=G)              # tokens HF would have emitted for a B=1 run
+        T = [int(v) - 1 for v in gen_len.tolist()]
+        assert min(T) >= 1, "an utterance produced no codes"
+        Tmax = max(T)
+        codes = codes[:, :Tmax]
+        if self.capture_latents:
+            latent = self.gpt.last_latents[:, :Tmax].contiguous()
+        else:
+            latent = self.gpt.forward(refer, rl, text, tl, codes, None, return_latent=True, clip_inputs=False,
+                                      mel_lengths=T)
+        cond = self.diffusion.get_conditioning(refer, rl)                        # model_24k.py:802
+        mel = do_spectrogram_diffusion(self.diffusion, self.infer_diffuser, latent, cond, temperature=1.0,
+                                       verbose=False, lengths=T, randn=hooks.get("randn"),
+                                       randn_like=hooks.get("randn_like"))       # model_24k.py:803
+        mel = denormalize_torch_mel(mel)                                           # model_24k.py:804
+        y_lengths = [4 * t for t in T]
+        wav = self.flowvae.infer(mel, y_lengths, noise_scale=noise_scale, randn_like=hooks.get("randn_like_zp"))
+        if trace is not None:
+            trace.update(codes=codes, T=T, latent=latent, cond=cond, mel=mel)
+        return wav, torch.tensor([1024 * t for t in T], device=dev)
+
+    @torch.no_grad()
+    def infer(self, text, text_length, refer, refer_lengths, noise_scale=0.667, **kw):
+        """vqvae/model_24k.py:774-810: batch item 0 only, returns wav [1,1,1024*T]."""
+        wav, wl = self.infer_batch(text[:1], [int(text_length[0])] if text_length is not None else [text.shape[1]],
+                                   refer[:1], [int(refer_lengths[0])], noise_scale=noise_scale, **kw)
+        return wav[:, :, :int(wl[0])]
+
+    @torch.no_grad()
+    def infer_flowvae(self, y, y_lengths, data=None, noise_scale=0.667, randn_like=None):
+        """vqvae/model_24k.py:848-863: denormalised mel [*,128,F] -> wav [1,1,256F] (batch item 0)."""
+        n = int(y_lengths[0])
+        return self.flowvae.infer(y[:1, :, :n], [n], noise_scale=noise_scale, randn_like=randn_like)
+
+
+def load_model(model_name, model_path, config_path=None, device="cuda", **kw):
+    """prepare/load_infer.py:8-34: build the model and load `ckpt['model']` or `ckpt['G']`.
+    `model_path` may also be 'synthetic:<seed>' (the seeded checkpoint generator; the published weights
+    are not available offline)."""
+    assert model_name in ("vqvae", "gpt")
+    if config_path is not None and os.path.exists(config_path):
+        cfg = json.load(open(config_path))
+        cfg.get("diffusion", {}).pop("g_channels", None)        # stale key
+        ref = synth.default_config()
+        for sec in ("gpt", "diffusion", "vaegan"):
+            if sec in cfg and sec in ref:
+                for k, v in ref[sec].items():
+                    if k in cfg[sec] and cfg[sec][k] != v:
+                        raise ValueError(f"config {sec}.{k}={cfg[sec][k]} differs from the architecture the kernels "
+                                         f"are built for ({v})")
+    if isinstance(model_path, str) and model_path.startswith("synthetic:"):
+        sd = synth.synth_state_dict(int(model_path.split(":")[1]), keys=synth.infer_path_key)
+    else:
+        ckpt = torch.load(model_path, map_location="cpu")
+        sd = ckpt["model"] if "model" in ckpt else ckpt["G"]
+    return SynthesizerTrn(sd, device=device, **kw)

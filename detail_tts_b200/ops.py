@@ -1,0 +1,162 @@
+"""Thin tensor-level wrappers over the C-ABI launches (detail_tts_b200/_lib.py).
+
+Everything here takes CUDA tensors that already live in the "rows" layout (channels-last [M, C],
+see include/dtts.h) and launches exactly one library kernel; no torch arithmetic happens on the
+synthesis path outside these wrappers except RNG draws and allocation.
+"""
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_NEW, ACT_LRELU, ACT_MISH, ACT_NONE, ACT_PAIR_GLU,  # noqa: F401
+                   ACT_PAIR_TANH_SIGMOID, ACT_RELU, ACT_SILU, ACT_TANH, BIAS_NONE,
+                   BIAS_RELPOS_TABLE, BIAS_WINDOW_REL)
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "rows tensors must be 2-D with unit channel stride"
+    return t.stride(0)
+
+
+class PackedConv:
+    """A conv/linear weight in GEMM form: W [taps*N, K] (tap-major, K contiguous), bias [N]."""
+    __slots__ = ("w", "bias", "N", "K", "taps", "shift0", "stride")
+
+    def __init__(self, w, bias, N, K, taps=1, shift0=0, stride=1):
+        self.w, self.bias, self.N, self.K = w, bias, N, K
+        self.taps, self.shift0, self.stride = taps, shift0, stride
+
+
+def gemm(A, pw, out32=None, out16=None, res=None, act=ACT_NONE, act_param=0.0, act16=ACT_NONE,
+         act16_param=0.0, alpha=1.0, accumulate=False, row_utt=None, bias_utt=None, out_row_map=None,
+         M=None, bias=True):
+    """out = alpha*(act(sum_taps A[m+shift] @ W_t^T + bias [+ bias_utt[row_utt]]) + res)."""
+    L = _lib.lib()
+    fn = "dtts_gemm_f16_tc" if A.dtype == torch.float16 else "dtts_gemm_f32"
+    assert pw.w.dtype == A.dtype, (pw.w.dtype, A.dtype)
+    assert A.shape[1] == pw.K, (A.shape, pw.K)
+    L.call(fn, A=A, W=pw.w, M=A.shape[0] if M is None else M, N=pw.N, K=pw.K, lda=_ld(A), ldw=_ld(pw.w),
+           taps=pw.taps, tap_shift0=pw.shift0, tap_stride=pw.stride,
+           bias=pw.bias if bias else None, bias_utt=bias_utt, row_utt=row_utt, out_row_map=out_row_map,
+           res=res, ldr=_ld(res) if res is not None else 0,
+           out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+           out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0,
+           act=act, act16=act16, act_param=act_param, act16_param=act16_param, alpha=alpha,
+           accumulate=int(accumulate))
+
+
+def groupnorm(x, lay, gamma, beta, out32=None, out16=None, groups=32, film=None, film_idx=None, act=ACT_NONE,
+              eps=1e-5):
+    """GroupNorm32 per utterance (+FiLM (scale|shift) rows [n, 2C]) (+SiLU)."""
+    C = gamma.numel()
+    _lib.lib().call("dtts_groupnorm", x=x, x_is_f16=int(x.dtype == torch.float16), ldx=_ld(x), C=C, groups=groups,
+                    n_utt=lay.n, max_len=lay.max_len, utt_off=lay.off, utt_len=lay.len, gamma=gamma, beta=beta,
+                    film_scale=film, film_shift=film[:, C:] if film is not None else None,
+                    ld_film=_ld(film) if film is not None else 0, film_idx=film_idx, act=act, eps=eps,
+                    out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0)
+
+
+def layernorm(x, gamma, beta, out32=None, out16=None, res=None, M=None, eps=1e-5, ldo32=None, row_utt=None):
+    C = gamma.numel()
+    _lib.lib().call("dtts_layernorm", x=x, ldx=_ld(x), M=x.shape[0] if M is None else M, C=C, gamma=gamma, beta=beta,
+                    eps=eps, res=res, ldr=_ld(res) if res is not None else 0,
+                    out_f32=out32, ldo32=(ldo32 if ldo32 is not None else _ld(out32)) if out32 is not None else 0,
+                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, row_utt=row_utt)
+
+
+def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max_k, scale, out32=None, out16=None,
+              head_stride=None, causal=False, causal_offset=None, bias_table=None, bias_half=0, rel_k=None,
+              rel_v=None, window=0, o_off=None, flash=False):
+    L = _lib.lib()
+    hs = head_dim if head_stride is None else head_stride
+    mode = BIAS_RELPOS_TABLE if bias_table is not None else (BIAS_WINDOW_REL if rel_k is not None else BIAS_NONE)
+    L.call("dtts_attention_f16_flash" if flash else "dtts_attention_f32", q=q, k=k, v=v,
+           is_f16=int(q.dtype == torch.float16), ldq=_ld(q), ldk=_ld(k), ldv=_ld(v), head_stride_q=hs,
+           head_stride_k=hs, head_stride_v=hs, n_utt=q_off.numel(), n_heads=n_heads, head_dim=head_dim,
+           q_off=q_off, q_len=q_len, k_off=k_off, k_len=k_len, max_q_len=max_q, max_k_len=max_k,
+           causal=int(causal), causal_offset=causal_offset, scale=scale, bias_mode=mode, bias_table=bias_table,
+           bias_half=bias_half, rel_k=rel_k, rel_v=rel_v, window=window,
+           out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+           out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, o_off=o_off)
+
+
+def bct_to_rows(src, lay, dst32=None, dst16=None, scale=1.0, shift=0.0):
+    B, C, T = src.shape
+    assert src.is_contiguous() and src.dtype == torch.float32
+    _lib.lib().call("dtts_bct_to_rows", src=src, B=B, C=C, T=T, utt_off=lay.off, utt_len=lay.len,
+                    dst_f32=dst32, ld32=_ld(dst32) if dst32 is not None else 0,
+                    dst_f16=dst16, ld16=_ld(dst16) if dst16 is not None else 0, scale=scale, shift=shift)
+
+
+def rows_to_bct(src, lay, dst, scale=1.0, shift=0.0):
+    B, C, T = dst.shape
+    assert dst.is_contiguous()
+    _lib.lib().call("dtts_rows_to_bct", src=src, ld=_ld(src), B=B, C=C, T=T, utt_off=lay.off, utt_len=lay.len,
+                    dst=dst, scale=scale, shift=shift)
+
+
+def eltwise(x, C, out32=None, out16=None, act=ACT_NONE, act_param=0.0, scale=1.0, row_utt=None):
+    _lib.lib().call("dtts_eltwise", x=x, ldx=_ld(x), M=x.shape[0], C=C, act=act, act_param=act_param, scale=scale,
+                    out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, row_utt=row_utt)
+
+
+def embed(ids, table, out, pos_table=None, pos=None, dst_row=None):
+    _lib.lib().call("dtts_embed", ids=ids, n=ids.numel(), table=table, dim=table.shape[1], pos_table=pos_table,
+                    pos=pos, out=out, ldo=_ld(out), dst_row=dst_row)
+
+
+def mean_rows(x, lay, out, C):
+    _lib.lib().call("dtts_mean_rows", x=x, ldx=_ld(x), C=C, n_utt=lay.n, utt_off=lay.off, utt_len=lay.len, out=out,
+                    ldo=_ld(out))
+
+
+def repeat_rows(x, lay, out, out_lay, repeat, C):
+    _lib.lib().call("dtts_repeat_rows", x=x, ldx=_ld(x), C=C, n_utt=lay.n, utt_off=lay.off, utt_len=lay.len,
+                    repeat=repeat, out=out, ldo=_ld(out), out_off=out_lay.off)
+
+
+class RowsLayout:
+    """Placement of n utterances in a rows buffer: utterance b owns rows [off[b], off[b]+len[b]),
+    `gap` zero separator rows before, between and after utterances (conv zero padding).  Offsets are
+    multiples of `align` so strided/paired views stay utterance-aligned."""
+
+    def __init__(self, lens, gap, device, align=1):
+        self.lens = [int(x) for x in lens]
+        self.n = len(self.lens)
+        self.gap = gap
+        offs, o = [], gap
+        for n in self.lens:
+            o = (o + align - 1) // align * align
+            offs.append(o)
+            o += n + gap
+        self.offs = offs
+        self.M = (o + align - 1) // align * align
+        self.max_len = max(self.lens) if self.lens else 0
+        self.device = device
+        self.off = torch.tensor(offs, dtype=torch.int32, device=device)
+        self.len = torch.tensor(self.lens, dtype=torch.int32, device=device)
+        self._row_utt = None
+
+    @property
+    def row_utt(self):
+        if self._row_utt is None:
+            ru = torch.empty(self.M, dtype=torch.int32, device=self.device)
+            _lib.lib().call("dtts_fill_row_utt", row_utt=ru, M=self.M, n_utt=self.n, utt_off=self.off,
+                            utt_len=self.len)
+            self._row_utt = ru
+        return self._row_utt
+
+    def scaled(self, factor):
+        """The layout after upsampling every row `factor` times (offsets and gaps scale too)."""
+        new = RowsLayout.__new__(RowsLayout)
+        new.lens = [n * factor for n in self.lens]
+        new.n, new.gap = self.n, self.gap * factor
+        new.offs = [o * factor for o in self.offs]
+        new.M = self.M * factor
+        new.max_len = self.max_len * factor
+        new.device = self.device
+        new.off = self.off * factor
+        new.len = self.len * factor
+        new._row_utt = None
+        return new

@@ -88,6 +88,7 @@ typedef struct {
   const float* gamma; const float* beta; float eps;
   const float* res; int ldr;      /* optional: normalises (x + res) */
   float* out_f32; int ldo32; void* out_f16; int ldo16;
+  const int* row_utt;             /* optional [M]: rows with -1 are separators and are not written */
 } dtts_layernorm_params;
 /* LayerNorm over channels of each row: GPT2Block ln_1/ln_2/ln_f, gpt/model.py:322 final_norm,
  * vqvae/modules/modules.py:36-48 (channel LayerNorm in enc_p). */
@@ -108,6 +109,7 @@ typedef struct {
   const float* bias_table; int bias_half;   /* RELPOS_TABLE: [n_heads, 2*bias_half+1] indexed clamp(j-i)+bias_half */
   const float* rel_k; const float* rel_v; int window;  /* WINDOW_REL: [2*window+1, head_dim] shared over heads */
   float* out_f32; int ldo32; void* out_f16; int ldo16;  /* [rows, n_heads*head_dim] head-major */
+  const int* o_off;           /* [n_utt] first output row of utterance b; NULL = q_off */
 } dtts_attention_params;
 /* softmax(scale*q.k + bias) v in exact fp32 on CUDA cores, one query per CTA.  Covers the small
  * attentions: GPT-2 causal attention incl. KV-cache decode (modeling_gpt2.py:54-72),
@@ -178,6 +180,7 @@ int dtts_eltwise(const dtts_eltwise_params* p, void* stream);          /* out = 
 typedef struct {
   const int64_t* ids; int n; const float* table; int dim; const float* pos_table; const int* pos; /* pos[n] or NULL */
   float* out; int ldo;
+  const int* dst_row;   /* optional [n]: output row of item i; NULL = i */
 } dtts_embed_params;
 int dtts_embed(const dtts_embed_params* p, void* stream);              /* gpt/model.py:134-136,517-519 */
 typedef struct {

@@ -415,7 +415,7 @@ def test_layout_and_small_ops(dlib):
     t = torch.tensor([0.0, 82.0, 3999.0], device=DEV)
     te = torch.zeros(3, 768, device=DEV)
     dlib.call("dtts_timestep_embedding", t=t, n=3, dim=768, out=te, ldo=768)
-    assert (te.cpu() - od.timestep_embedding(t.cpu())).abs().max().item() < 2e-4
+    assert (te.cpu() - od.timestep_embedding(t.cpu())).abs().max().item() < 5e-4  # fp32 angle up to 4e3 rad
     # embed
     table, ptab = torch.randn(300, 64, generator=g, device=DEV), torch.randn(50, 64, generator=g, device=DEV)
     ids = torch.randint(0, 300, (20,), generator=g, device=DEV)
