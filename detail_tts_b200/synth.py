@@ -93,6 +93,8 @@ def _draw(key, shape, seed, sd):
             gain = 0.5   # zero-init in the reference; drawn non-zero (see module docstring)
         if key == "diffusion.out.2.weight":
             gain = 0.4   # keeps the sampled mel away from the [-1,1] clamp (less saturated parity)
+        if key == "dec.conv_post.weight":
+            gain = 0.06  # waveform RMS ~0.06 (speech level, tanh unsaturated) instead of a clipped ~0.6
         return randn(gain / math.sqrt(fan_in))
     return randn(0.02)
 
