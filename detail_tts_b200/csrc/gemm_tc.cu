@@ -11,6 +11,7 @@
 // separator rows of the rows layout implement the reference's per-utterance zero padding.
 //
 // Replaces nn.Conv1d/nn.Linear/ConvTranspose1d + their eager epilogues (see include/dtts.h).
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -21,17 +22,20 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements = 128 bytes = one swizzle span
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2.. epilogue
+constexpr int EPI_LD = 36;        // padded fp32 row of the per-warp 32x32 transpose staging tile
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
 
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (208 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = 2 * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -123,7 +127,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride) {
+               const EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride, const int debug) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries of the SHARED address space
@@ -134,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
   uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * C::STAGES + 4);
+  float* epi_stage = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -211,20 +216,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // ================================ epilogue warps ===============================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int cpar = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks c = cpar, cpar+2, ...
+    float* st = epi_stage + (warp - 2) * 32 * EPI_LD;
+    // fast path: plain/act epilogue on 4 consecutive columns per lane, everything 16-byte aligned
+    const bool fast = epi.act < DTTS_ACT_PAIR_TANH_SIGMOID && !epi.out_row_map && !epi.accumulate && (epi.N & 3) == 0 &&
+                      (!epi.res || ((epi.ldr & 3) == 0 && (((uintptr_t)epi.res) & 15) == 0)) &&
+                      (!epi.out_f32 || ((epi.ldo32 & 3) == 0 && (((uintptr_t)epi.out_f32) & 15) == 0)) &&
+                      (!epi.out_f16 || ((epi.ldo16 & 3) == 0 && (((uintptr_t)epi.out_f16) & 7) == 0)) &&
+                      (!epi.bias || (((uintptr_t)epi.bias) & 15) == 0) && (!epi.bias_utt || (((uintptr_t)epi.bias_utt) & 15) == 0);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      // TMEM lane = output row.  Each 32x32 chunk is transposed through a per-warp shared-memory tile so
+      // that a lane owns 4 CONSECUTIVE columns of a row: residual loads and fp32/fp16 stores are then
+      // 128 B / 64 B contiguous per row (8 lanes); all global loads of a chunk are issued before use.
+      const int mrow = m0 + q * 32 + (lane >> 3);   // + it*4
+      const int cc = (lane & 7) * 4;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cpar; c < (debug == 1 ? 0 : BN / 32); c += 2) {
+        const int n = n0 + c * 32 + cc;
+        if (n0 + c * 32 >= epi.N) break;
         float v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         tmem_ld32(taddr, v);
-        epilogue_chunk<32>(epi, m, n0 + c * 32, v);
+        float4* srow = reinterpret_cast<float4*>(st + lane * EPI_LD);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+        if (fast) {
+          const bool ncol_ok = n < epi.N;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (epi.bias && ncol_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
+          int ru[8];
+          float4 rs[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = mrow + it * 4;
+            int u = -1;
+            if (m < epi.M && ncol_ok) u = epi.row_utt ? __ldg(epi.row_utt + m) : 0;
+            ru[it] = u;
+            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u >= 0 && epi.res) rs[it] = *reinterpret_cast<const float4*>(epi.res + (long)m * epi.ldr + n);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (ru[it] < 0) continue;
+            const int m = mrow + it * 4;
+            const float4 t = *reinterpret_cast<const float4*>(st + (it * 4 + (lane >> 3)) * EPI_LD + cc);
+            float w[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
+            if (epi.bias_utt) {
+              const float4 bu = __ldg(reinterpret_cast<const float4*>(epi.bias_utt + (long)ru[it] * epi.N + n));
+              w[0] += bu.x; w[1] += bu.y; w[2] += bu.z; w[3] += bu.w;
+            }
+            if (epi.act != DTTS_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) w[j] = act_apply(epi.act, w[j], epi.act_param);
+            }
+            w[0] = epi.alpha * (w[0] + rs[it].x); w[1] = epi.alpha * (w[1] + rs[it].y);
+            w[2] = epi.alpha * (w[2] + rs[it].z); w[3] = epi.alpha * (w[3] + rs[it].w);
+            if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + (long)m * epi.ldo32 + n) = make_float4(w[0], w[1], w[2], w[3]);
+            if (epi.out_f16) {
+              if (epi.act16 != DTTS_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[j] = act_apply(epi.act16, w[j], epi.act16_param);
+              }
+              __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(epi.out_f16 + (long)m * epi.ldo16 + n) = pk;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const float4 t = *reinterpret_cast<const float4*>(st + r * EPI_LD + cc);
+            float w[4] = {t.x, t.y, t.z, t.w};
+            epilogue_chunk<4>(epi, m0 + q * 32 + r, n, w);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -303,6 +379,7 @@ int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorM
 }
 
 int g_sm_count = 0;
+int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
 template <int BN>
 int launch(const dtts_gemm_params* p, cudaStream_t st) {
@@ -321,7 +398,7 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, BN);
   const int grid = tiles < g_sm_count ? tiles : g_sm_count;
   EpiParams e = make_epi(p);
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride);
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride, g_debug);
   DTTS_CHECK_LAUNCH("gemm_tc");
   return 0;
 }
@@ -337,6 +414,10 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   DTTS_REQUIRE(!(p->bias_utt && !p->row_utt), "gemm_f16_tc: bias_utt requires row_utt");
   DTTS_REQUIRE(p->out_f32 || p->out_f16, "gemm_f16_tc: no output");
   DTTS_REQUIRE(!(p->act >= DTTS_ACT_PAIR_TANH_SIGMOID && (p->N & 1)), "gemm_f16_tc: pair activation needs even N");
+  if (g_debug < 0) {
+    const char* d = getenv("DTTS_GEMM_DEBUG");
+    g_debug = d ? atoi(d) : 0;
+  }
   if (!g_sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
