@@ -294,7 +294,12 @@ def main():
     e2e_value = audio_s_total * args.steps / (ms_e2e * 1e-3)
 
     roof = None
+    stage_ms = None
     if rank == 0:
+        tr = {"timing": True}
+        torch.manual_seed(1)
+        model.infer_batch(text_d, tl_m, refer_d, rl_m, trace=tr, **kw)
+        stage_ms = {k: round(v, 2) for k, v in tr["stage_ms"].items()}
         roof = gemm_roofline(model, lib, pk)
         roof["peak_source"] = f"{pk_src} (bf16_tflops_sustained: kernel timed inside a long step)"
     cpu = None
@@ -315,7 +320,7 @@ def main():
                           "l2": "per-step working set (activations of 2*B*280 rows x 768 ch + 300 MB weights) exceeds the 126 MB L2; no explicit flush"},
                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+               "gpu_launches": launches, "stage_ms": stage_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

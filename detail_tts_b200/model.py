@@ -51,6 +51,14 @@ class SynthesizerTrn:
         `hooks`: optional dict of RNG overrides {multinomial, randn, randn_like, randn_like_zp} (tests)."""
         hooks = hooks or {}
         dev = self.device
+        marks = []
+
+        def mark(name):
+            if trace is not None and trace.get("timing"):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
         B = text.shape[0]
         tl = [int(v) for v in text_lengths]
         rl = [int(v) for v in refer_lengths]
@@ -62,6 +70,7 @@ class SynthesizerTrn:
         if suppress_eos:
             kw["suppress_tokens"] = [STOP_MEL]
         codes = self.gpt.inference_speech_tortoise(refer, rl, text, **kw)
+        mark("gpt")
         # model_24k.py:795: codes[:, :-1] drops the stop token (or the last token when the cap was hit)
         G = codes.shape[1]
         fin = codes == STOP_MEL
@@ -76,15 +85,22 @@ class SynthesizerTrn:
         else:
             latent = self.gpt.forward(refer, rl, text, tl, codes, None, return_latent=True, clip_inputs=False,
                                       mel_lengths=T)
+        mark("latents")
         cond = self.diffusion.get_conditioning(refer, rl)                        # model_24k.py:802
+        mark("diff_cond")
         mel = do_spectrogram_diffusion(self.diffusion, self.infer_diffuser, latent, cond, temperature=1.0,
                                        verbose=False, lengths=T, randn=hooks.get("randn"),
                                        randn_like=hooks.get("randn_like"))       # model_24k.py:803
         mel = denormalize_torch_mel(mel)                                           # model_24k.py:804
+        mark("diffusion")
         y_lengths = [4 * t for t in T]
         wav = self.flowvae.infer(mel, y_lengths, noise_scale=noise_scale, randn_like=hooks.get("randn_like_zp"))
+        mark("flowvae_vocoder")
         if trace is not None:
             trace.update(codes=codes, T=T, latent=latent, cond=cond, mel=mel)
+            if marks:
+                torch.cuda.synchronize()
+                trace["stage_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         return wav, torch.tensor([1024 * t for t in T], device=dev)
 
     @torch.no_grad()

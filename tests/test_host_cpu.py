@@ -1,0 +1,209 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/dtts.h declares (no compute calls
+without a GPU), the weight packers against torch's own conv ops through a pure-torch emulation of the
+multi-tap GEMM contract, the sampler constants, and utterance sharding over gloo (world_size 2)."""
+import ctypes
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from detail_tts_b200 import _lib, pack, synth
+from detail_tts_b200 import dist as ddist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_symbols_and_struct_sizes():
+    from detail_tts_b200 import build
+    path = build.build_lib()
+    structs, funcs = _lib.parse_header()
+    assert len(funcs) >= 19 and len(structs) >= 17
+    cdll = ctypes.CDLL(path)
+    for fname, sname in funcs:
+        assert hasattr(cdll, fname), fname
+        assert sname in structs
+    for extra in ("dtts_abi_version", "dtts_last_error", "dtts_sizeof", "dtts_kernel_launches", "dtts_device_info"):
+        assert hasattr(cdll, extra)
+    L = _lib.Lib(path)           # cross-checks every struct size against dtts_sizeof()
+    assert L.cdll.dtts_abi_version() == 1
+    assert L.launches() == 0
+
+
+def test_product_path_has_no_cpu_fallback():
+    from detail_tts_b200.model import SynthesizerTrn
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        SynthesizerTrn({}, device="cuda")
+
+
+def test_product_does_not_import_oracle():
+    import re
+    for root, _, files in os.walk(os.path.join(ROOT, "detail_tts_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f
+
+
+def gemm_emul(A, pw, act=None):
+    """Pure-torch statement of the dtts_gemm contract (taps over rows) for packer tests."""
+    M = A.shape[0]
+    acc = torch.zeros(M, pw.N, dtype=torch.float64)
+    W = pw.w.double()
+    for t in range(pw.taps):
+        sh = pw.shift0 + t * pw.stride
+        As = torch.zeros(M, pw.K, dtype=torch.float64)
+        lo, hi = max(0, -sh), min(M, M - sh)
+        if hi > lo:
+            As[lo:hi, :A.shape[1]] = A[lo + sh:hi + sh].double()
+        acc += As @ W[t * pw.N:(t + 1) * pw.N].T
+    if pw.bias is not None:
+        acc += pw.bias.double()
+    return acc
+
+
+@pytest.mark.parametrize("cin,cout,k,dil", [(24, 40, 3, 1), (16, 16, 7, 3), (12, 12, 11, 5), (13, 9, 5, 1)])
+def test_pack_conv1d(cin, cout, k, dil):
+    g = torch.Generator().manual_seed(k)
+    w, b = torch.randn(cout, cin, k, generator=g), torch.randn(cout, generator=g)
+    x = torch.randn(1, cin, 50, generator=g)
+    pad = (k * dil - dil) // 2
+    ref = F.conv1d(x, w, b, padding=pad, dilation=dil)[0].t()
+    pw = pack.pack_conv1d(w, b, torch.float32, "cpu", padding=pad, dilation=dil, n_pad=8)
+    # rows layout with `pad` zero separator rows on both sides
+    rows = torch.zeros(50 + 2 * pad, pw.K)
+    rows[pad:pad + 50, :cin] = x[0].t()
+    out = gemm_emul(rows, pw)[pad:pad + 50, :cout]
+    assert (out - ref.double()).abs().max() < 2e-4
+    if pw.N > cout:
+        assert gemm_emul(rows, pw)[:, cout:].abs().max() == 0      # padded output channels stay zero
+
+
+@pytest.mark.parametrize("cin,cout,k,u", [(20, 10, 16, 8), (10, 5, 8, 4), (6, 3, 2, 2)])
+def test_pack_conv_transpose1d(cin, cout, k, u):
+    g = torch.Generator().manual_seed(u)
+    w, b = torch.randn(cin, cout, k, generator=g), torch.randn(cout, generator=g)
+    T = 17
+    x = torch.randn(1, cin, T, generator=g)
+    ref = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)[0].t()         # [T*u, cout]
+    pw = pack.pack_conv_transpose1d(w, b, torch.float32, "cpu", stride=u, padding=(k - u) // 2)
+    gap = 2
+    rows = torch.zeros(T + 2 * gap, pw.K)
+    rows[gap:gap + T, :cin] = x[0].t()
+    out = gemm_emul(rows, pw)                                                           # [M, u*Np]
+    Np = pw.N // u
+    up = out.reshape(-1, Np)[gap * u:(gap + T) * u, :cout]
+    assert (up - ref.double()).abs().max() < 2e-4
+
+
+def test_pack_conv1d_stride2():
+    g = torch.Generator().manual_seed(3)
+    w, b = torch.randn(14, 6, 3, generator=g), torch.randn(14, generator=g)
+    for R in (20, 21):
+        x = torch.randn(1, 6, R, generator=g)
+        ref = F.conv1d(x, w, b, stride=2, padding=1)[0].t()
+        pw = pack.pack_conv1d_stride2(w, b, torch.float32, "cpu")
+        Kp = pw.K // 2
+        off = 4
+        rows = torch.zeros(off + R + 4 + (R % 2), Kp)
+        rows[off:off + R, :6] = x[0].t()
+        paired = rows.reshape(-1, 2 * Kp)
+        out = gemm_emul(paired, pw)[off // 2:off // 2 + (R + 1) // 2]
+        assert out.shape[0] == ref.shape[0]
+        assert (out - ref.double()).abs().max() < 2e-4
+
+
+def test_weight_norm_and_interleave():
+    g = torch.Generator().manual_seed(1)
+    v, gg = torch.randn(8, 4, 5, generator=g), torch.rand(8, 1, 1, generator=g) + 0.5
+    lin = torch.nn.utils.weight_norm(torch.nn.Conv1d(4, 8, 5), dim=0)
+    with torch.no_grad():
+        lin.weight_v.copy_(v)
+        lin.weight_g.copy_(gg)
+    x = torch.randn(1, 4, 9, generator=g)
+    ref = F.conv1d(x, pack.fold_weight_norm(v, gg), lin.bias)
+    assert (lin(x) - ref).abs().max() < 2e-4
+    w, b, idx = pack.interleave_halves(torch.arange(8.)[:, None], torch.arange(8.))
+    assert w[:, 0].tolist() == [0, 4, 1, 5, 2, 6, 3, 7] and b.tolist() == w[:, 0].tolist()
+
+
+def test_spaced_diffusion_constants(golden):
+    import numpy as np
+    from detail_tts_b200.diffusion import SpacedDiffusion, space_timesteps
+    d = SpacedDiffusion(use_timesteps=space_timesteps(4000, [50]))
+    tab = golden["sched"]["table"].numpy()
+    assert d.timestep_map == [int(v) for v in tab[:, 0]]
+    assert np.array_equal(tab[:, 1], d.sqrt_recip_alphas_cumprod)
+    assert np.array_equal(tab[:, 6], d.posterior_mean_coef2)
+    c = d.step_constants(49)
+    assert c["nonzero"] == 1.0 and abs(c["cfk"] - 2 * (1 - 49 / 50)) < 1e-12 and d.step_constants(0)["nonzero"] == 0.0
+
+
+def test_synthetic_checkpoint_layout():
+    m = synth.manifest()
+    keys = [e["key"] for e in m["entries"]]
+    assert len(keys) == 1278 and "gpt.gpt.h.0.attn.c_attn.weight" in keys
+    sd = synth.synth_state_dict(0, keys=lambda k: k.startswith("dec.ups.0"))
+    assert sd["dec.ups.0.weight_v"].shape == (400, 200, 16) and sd["dec.ups.0.weight_g"].shape == (400, 1, 1)
+    sd2 = synth.synth_state_dict(0, keys=lambda k: k.startswith("dec.ups.0"))
+    assert torch.equal(sd["dec.ups.0.weight_v"], sd2["dec.ups.0.weight_v"])
+
+
+def test_shard_slices_balance():
+    shards = ddist.shard_slices(128, 8, costs=[30 + (i * 7) % 41 for i in range(128)])
+    assert sorted(sum(shards, [])) == list(range(128)) and all(len(s) == 16 for s in shards)
+    costs = [30 + (i * 7) % 41 for i in range(128)]
+    tot = [sum(costs[i] for i in s) for s in shards]
+    assert max(tot) - min(tot) <= 41
+    assert ddist.shard_slices(3, 4) == [[0], [1], [2], []]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, L, R = 5, 7, 12
+    g = torch.Generator().manual_seed(0)
+    text = torch.randint(0, 255, (B, L), generator=g, dtype=torch.int32)
+    refer = torch.randn(B, 128, R, generator=g)
+    tl, rl = [7, 5, 6, 7, 4], [12, 10, 9, 12, 11]
+    if rank == 0:
+        t, tlen, rf, rlen, mine, shards = ddist.scatter_inputs(text, tl, refer, rl, "cpu")
+    else:
+        t, tlen, rf, rlen, mine, shards = ddist.scatter_inputs(None, None, None, None, "cpu")
+    ok = all(torch.equal(t[i], text[j]) and int(tlen[i]) == tl[j] and torch.equal(rf[i], refer[j]) and int(rlen[i]) == rl[j]
+             for i, j in enumerate(mine))
+    # fake synthesis: waveform = utterance index, length = 10 + index
+    wav = torch.stack([torch.full((1, 20), float(j)) for j in mine]) if mine else torch.zeros(0, 1, 20)
+    wl = torch.tensor([10 + j for j in mine], dtype=torch.int64)
+    full, lens = ddist.gather_waveforms(wav, wl, shards, 20, "cpu")
+    if rank == 0:
+        ok = ok and all(float(full[j, 0, 0]) == j for j in range(B)) and lens.tolist() == [10 + j for j in range(B)]
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_scatter_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
