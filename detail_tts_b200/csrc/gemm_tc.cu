@@ -219,76 +219,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int cpar = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks c = cpar, cpar+2, ...
     float* st = epi_stage + (warp - 2) * 32 * EPI_LD;
+    const int cc = (lane & 7) * 4;
     // fast path: plain/act epilogue on 4 consecutive columns per lane, everything 16-byte aligned
     const bool fast = epi.act < DTTS_ACT_PAIR_TANH_SIGMOID && !epi.out_row_map && !epi.accumulate && (epi.N & 3) == 0 &&
                       (!epi.res || ((epi.ldr & 3) == 0 && (((uintptr_t)epi.res) & 15) == 0)) &&
                       (!epi.out_f32 || ((epi.ldo32 & 3) == 0 && (((uintptr_t)epi.out_f32) & 15) == 0)) &&
                       (!epi.out_f16 || ((epi.ldo16 & 3) == 0 && (((uintptr_t)epi.out_f16) & 7) == 0)) &&
                       (!epi.bias || (((uintptr_t)epi.bias) & 15) == 0) && (!epi.bias_utt || (((uintptr_t)epi.bias_utt) & 15) == 0);
+    // lean path (every diffusion / vocoder conv): bias + residual + alpha, fp32 and/or fp16 stores (optional
+    // leaky-ReLU on the fp16 copy).  ~25 instructions per 4 outputs: pointers advance by constant strides, row
+    // validity comes from a per-tile bitmask loaded while the MMAs still run, all residual loads are issued first.
+    const bool lean = fast && epi.act == DTTS_ACT_NONE && (epi.act16 == DTTS_ACT_NONE || epi.act16 == DTTS_ACT_LRELU) && !epi.bias_utt;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
+      const int mrow = m0 + q * 32 + (lane >> 3);   // + it*4
+      uint32_t vmask = 0;
+      if (lean) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = mrow + it * 4;
+          const bool ok = m < epi.M && (!epi.row_utt || __ldg(epi.row_utt + m) >= 0);
+          vmask |= ok ? (1u << it) : 0u;
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      // TMEM lane = output row.  Each 32x32 chunk is transposed through a per-warp shared-memory tile so
-      // that a lane owns 4 CONSECUTIVE columns of a row: residual loads and fp32/fp16 stores are then
-      // 128 B / 64 B contiguous per row (8 lanes); all global loads of a chunk are issued before use.
-      const int mrow = m0 + q * 32 + (lane >> 3);   // + it*4
-      const int cc = (lane & 7) * 4;
+      // TMEM lane = output row.  Each 32x32 chunk is transposed through a per-warp shared-memory tile so that
+      // a lane owns 4 CONSECUTIVE columns of a row: residual loads and fp32/fp16 stores are 128 B / 64 B
+      // contiguous per row (8 lanes).
 #pragma unroll 1
       for (int c = cpar; c < (debug == 1 ? 0 : BN / 32); c += 2) {
         const int n = n0 + c * 32 + cc;
         if (n0 + c * 32 >= epi.N) break;
-        float v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        tmem_ld32(taddr, v);
-        float4* srow = reinterpret_cast<float4*>(st + lane * EPI_LD);
+        if (debug != 3) {
+          float v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+          tmem_ld32(taddr, v);
+          float4* srow = reinterpret_cast<float4*>(st + lane * EPI_LD);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        __syncwarp();
-        if (fast) {
-          const bool ncol_ok = n < epi.N;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (epi.bias && ncol_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
-          int ru[8];
-          float4 rs[8];
+          for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+        }
+        if (debug == 2) continue;
+        if (lean) {
+          if (n < epi.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
+            float4 rs[8];
+            if (epi.res) {
+              const float* rp = epi.res + (size_t)mrow * epi.ldr + n;
+              const size_t rstep = (size_t)4 * epi.ldr;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int m = mrow + it * 4;
-            int u = -1;
-            if (m < epi.M && ncol_ok) u = epi.row_utt ? __ldg(epi.row_utt + m) : 0;
-            ru[it] = u;
-            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u >= 0 && epi.res) rs[it] = *reinterpret_cast<const float4*>(epi.res + (long)m * epi.ldr + n);
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            if (ru[it] < 0) continue;
-            const int m = mrow + it * 4;
-            const float4 t = *reinterpret_cast<const float4*>(st + (it * 4 + (lane >> 3)) * EPI_LD + cc);
-            float w[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
-            if (epi.bias_utt) {
-              const float4 bu = __ldg(reinterpret_cast<const float4*>(epi.bias_utt + (long)ru[it] * epi.N + n));
-              w[0] += bu.x; w[1] += bu.y; w[2] += bu.z; w[3] += bu.w;
-            }
-            if (epi.act != DTTS_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) w[j] = act_apply(epi.act, w[j], epi.act_param);
-            }
-            w[0] = epi.alpha * (w[0] + rs[it].x); w[1] = epi.alpha * (w[1] + rs[it].y);
-            w[2] = epi.alpha * (w[2] + rs[it].z); w[3] = epi.alpha * (w[3] + rs[it].w);
-            if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + (long)m * epi.ldo32 + n) = make_float4(w[0], w[1], w[2], w[3]);
-            if (epi.out_f16) {
-              if (epi.act16 != DTTS_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = act_apply(epi.act16, w[j], epi.act16_param);
+              for (int it = 0; it < 8; ++it) {
+                rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((vmask >> it) & 1u) rs[it] = *reinterpret_cast<const float4*>(rp);
+                rp += rstep;
               }
-              __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(epi.out_f16 + (long)m * epi.ldo16 + n) = pk;
+            }
+            float* o32 = epi.out_f32 ? epi.out_f32 + (size_t)mrow * epi.ldo32 + n : nullptr;
+            __half* o16 = epi.out_f16 ? epi.out_f16 + (size_t)mrow * epi.ldo16 + n : nullptr;
+            const size_t s32 = (size_t)4 * epi.ldo32, s16 = (size_t)4 * epi.ldo16;
+            const float* sp = st + (lane >> 3) * EPI_LD + cc;
+            const bool lrelu16 = epi.act16 == DTTS_ACT_LRELU;
+            const float slope = epi.act16_param, alpha = epi.alpha;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if ((vmask >> it) & 1u) {
+                const float4 t = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD);
+                float w0 = t.x + b4.x, w1 = t.y + b4.y, w2 = t.z + b4.z, w3 = t.w + b4.w;
+                if (epi.res) { w0 += rs[it].x; w1 += rs[it].y; w2 += rs[it].z; w3 += rs[it].w; }
+                if (alpha != 1.0f) { w0 *= alpha; w1 *= alpha; w2 *= alpha; w3 *= alpha; }
+                if (o32) *reinterpret_cast<float4*>(o32) = make_float4(w0, w1, w2, w3);
+                if (o16) {
+                  if (lrelu16) {
+                    w0 = w0 > 0.f ? w0 : w0 * slope; w1 = w1 > 0.f ? w1 : w1 * slope;
+                    w2 = w2 > 0.f ? w2 : w2 * slope; w3 = w3 > 0.f ? w3 : w3 * slope;
+                  }
+                  __half2 h0 = __floats2half2_rn(w0, w1), h1 = __floats2half2_rn(w2, w3);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                  *reinterpret_cast<uint2*>(o16) = pk;
+                }
+              }
+              if (o32) o32 += s32;
+              if (o16) o16 += s16;
             }
           }
         } else {

@@ -107,6 +107,107 @@ groupnorm_kernel(const T* __restrict__ x, int ldx, int C, int cpg, const int* __
   }
 }
 
+// Register-resident variant for the diffusion hot loop (24 channels/group, utterances up to
+// GNR_MAXR * rows-per-sweep frames): one CTA = (utterance, 2 groups); the whole [T, 48] strip is loaded
+// into registers with every load in flight at once (HBM-latency bound otherwise), statistics are exact
+// two-pass (mean, then centred sum of squares) from registers, and the normalised operand is written
+// straight from registers: x is read from HBM exactly once and nothing is staged in shared memory.
+constexpr int GNR_GPC = 2;     // groups per CTA
+constexpr int GNR_MAXR = 16;   // rows per thread
+constexpr int GNR_THREADS = 256;
+
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < GNR_THREADS / 32; ++i) { t.x += sh[i].x; t.y += sh[i].y; }
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GNR_THREADS)
+groupnorm_reg_kernel(const T* __restrict__ x, int ldx, int cpg, const int* __restrict__ utt_off,
+                     const int* __restrict__ utt_len, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ film_scale, const float* __restrict__ film_shift, int ld_film,
+                     const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
+                     __half* __restrict__ out16, int ldo16) {
+  __shared__ float2 red[GNR_THREADS / 32];
+  const int b = blockIdx.y;
+  const int cw = GNR_GPC * cpg;
+  const int c0 = blockIdx.x * cw;
+  const int Q = cw >> 2;
+  const int rs = GNR_THREADS / Q;
+  const int col4 = threadIdx.x % Q, rsub = threadIdx.x / Q;
+  const bool active = rsub < rs;
+  const int g = (col4 * 4) / cpg;   // 0 or 1
+  const int T_ = utt_len[b];
+  const long row0 = utt_off[b];
+  const T* xb = x + row0 * ldx + c0 + col4 * 4;
+  float4 v[GNR_MAXR];
+#pragma unroll
+  for (int i = 0; i < GNR_MAXR; ++i) {
+    const int r = rsub + i * rs;
+    v[i] = (active && r < T_) ? load4<T>(xb + (long)r * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < GNR_MAXR; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float inv_n = 1.0f / ((float)T_ * cpg);
+  float2 sm = block_sum2(make_float2(g == 0 ? s : 0.f, g == 1 ? s : 0.f), red);
+  const float mean = (g == 0 ? sm.x : sm.y) * inv_n;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < GNR_MAXR; ++i) {
+    const int r = rsub + i * rs;
+    if (active && r < T_) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  }
+  float2 sq = block_sum2(make_float2(g == 0 ? ss : 0.f, g == 1 ? ss : 0.f), red);
+  const float rstd = rsqrtf((g == 0 ? sq.x : sq.y) * inv_n + eps);
+  if (!active) return;
+  const int c = c0 + col4 * 4;
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+  float A_[4] = {rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w};
+  float B_[4] = {be.x - mean * A_[0], be.y - mean * A_[1], be.z - mean * A_[2], be.w - mean * A_[3]};
+  if (film_scale) {   // (x*A+B)*(1+fs)+fb = x*A(1+fs) + B(1+fs)+fb
+    const long fr = film_idx ? film_idx[b] : b;
+    const float4 fs = *reinterpret_cast<const float4*>(film_scale + fr * ld_film + c);
+    const float4 fb = *reinterpret_cast<const float4*>(film_shift + fr * ld_film + c);
+    const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { A_[q] *= f1[q]; B_[q] = B_[q] * f1[q] + f0[q]; }
+  }
+#pragma unroll
+  for (int i = 0; i < GNR_MAXR; ++i) {
+    const int r = rsub + i * rs;
+    if (r >= T_) break;
+    float y[4] = {v[i].x * A_[0] + B_[0], v[i].y * A_[1] + B_[1], v[i].z * A_[2] + B_[2], v[i].w * A_[3] + B_[3]};
+    if (act == DTTS_ACT_SILU) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[q] = y[q] * sigmoidf_(y[q]);
+    }
+    const long orow = row0 + r;
+    if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(out16 + orow * ldo16 + c) = pk;
+    }
+  }
+}
+
 constexpr int LN_MAXE = 32;  // C <= 1024
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
@@ -166,6 +267,28 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
     max_smem = 160 * 1024;
     cudaFuncSetAttribute(groupnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(groupnorm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  }
+  cudaStream_t st0 = (cudaStream_t)stream;
+  {
+    // register-resident fast path (see groupnorm_reg_kernel)
+    const int Qr = GNR_GPC * cpg / 4;
+    const int rs = Qr > 0 ? GNR_THREADS / Qr : 0;
+    const bool aligned = ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->x)) & 15) == 0 &&
+                         (!p->film_scale || (((((uintptr_t)p->film_scale) | ((uintptr_t)p->film_shift)) & 15) == 0 && p->ld_film % 4 == 0)) &&
+                         (!p->out_f32 || (((uintptr_t)p->out_f32) & 15) == 0) && (!p->out_f16 || (((uintptr_t)p->out_f16) & 7) == 0);
+    if (p->groups % GNR_GPC == 0 && rs > 0 && p->max_len > 0 && p->max_len <= GNR_MAXR * rs && aligned && cpg % 4 == 0 && cpg <= 32) {
+      dim3 grid(p->groups / GNR_GPC, p->n_utt);
+      if (p->x_is_f16)
+        groupnorm_reg_kernel<__half><<<grid, GNR_THREADS, 0, st0>>>(
+            (const __half*)p->x, p->ldx, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
+            p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
+      else
+        groupnorm_reg_kernel<float><<<grid, GNR_THREADS, 0, st0>>>(
+            (const float*)p->x, p->ldx, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
+            p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
+      DTTS_CHECK_LAUNCH("groupnorm_reg");
+      return 0;
+    }
   }
   // cache as many rows as fit; the caller passes the longest utterance via utt_len on device, so
   // size for the budget (rows beyond cache_rows are re-read from L2).
