@@ -71,6 +71,22 @@ class Plan:
             if rc != 0:
                 raise DttsError(f"{fn.__name__} failed ({rc}): {self.lib.last_error()}")
 
+    def profile(self, stream=None):
+        """Run once with a CUDA-event pair around every launch; returns [(entry point, struct, ms)]."""
+        st = torch.cuda.current_stream()
+        sp = ctypes.c_void_p(st.cuda_stream)
+        evs = []
+        for fn, s in self.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = fn(ctypes.byref(s), sp)
+            if rc != 0:
+                raise DttsError(f"{fn.__name__} failed ({rc}): {self.lib.last_error()}")
+            e1.record(st)
+            evs.append((fn.__name__, s, e0, e1))
+        torch.cuda.synchronize()
+        return [(n, s, a.elapsed_time(b)) for n, s, a, b in evs]
+
     def __len__(self):
         return len(self.calls)
 

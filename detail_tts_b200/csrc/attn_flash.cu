@@ -14,7 +14,10 @@ namespace {
 
 constexpr int HD = 48;
 constexpr int LDS = 56;     // padded smem row (halfs): 112 B rows -> conflict-free ldmatrix
-constexpr int BQ = 64, BKV = 64;
+constexpr int BQ = 96, BKV = 48;   // 6 warps x 16 queries; 48-key tiles: F=280 pads to 288 (2.9 %) on both axes
+constexpr int NWARP = BQ / 16;
+constexpr int NTHR = NWARP * 32;
+constexpr int NT = BKV / 8;        // score n-tiles per key tile
 constexpr int MAX_BIAS = 513;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -40,8 +43,18 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(128)
+// Scores are kept in the log2 domain: s2 = (q.k)*scale*log2e + bias*log2e, p = 2^(s2 - m2).  The scale is
+// applied to the fp32 accumulator (one FMUL fused with the bias add as an FFMA); the bias table is staged
+// pre-multiplied by log2e.  Key tiles entirely beyond the clamp distance of the table (|key - query| >=
+// bias_half for every pair) take a tile-uniform bias with no table lookups; the key mask is only evaluated
+// on the last key tile.
+__global__ void __launch_bounds__(NTHR)
 flash48_kernel(const dtts_attention_params p) {
   __shared__ __align__(16) __half sQ[BQ][LDS];
   __shared__ __align__(16) __half sK[2][BKV][LDS];
@@ -56,19 +69,20 @@ flash48_kernel(const dtts_attention_params p) {
   const __half* qg = (const __half*)p.q + (long)p.q_off[b] * p.ldq + (long)h * p.head_stride_q;
   const __half* kg = (const __half*)p.k + (long)p.k_off[b] * p.ldk + (long)h * p.head_stride_k;
   const __half* vg = (const __half*)p.v + (long)p.k_off[b] * p.ldv + (long)h * p.head_stride_v;
+  const float LOG2E = 1.4426950408889634f;
 
-  // Q tile + bias table
-  for (int c = tid; c < BQ * 6; c += 128) {
+  for (int c = tid; c < BQ * 6; c += NTHR) {
     const int r = c / 6, ch = (c % 6) * 8;
     if (q0 + r < qlen) cp_async16(&sQ[r][ch], qg + (long)(q0 + r) * p.ldq + ch);
     else *reinterpret_cast<uint4*>(&sQ[r][ch]) = make_uint4(0, 0, 0, 0);
   }
-  const int nb = p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? 2 * p.bias_half + 1 : 0;
-  for (int i = tid; i < nb; i += 128) sBias[i] = p.bias_table[h * nb + i];
+  const int half = p.bias_half;
+  const int nb = p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? 2 * half + 1 : 0;
+  for (int i = tid; i < nb; i += NTHR) sBias[i] = p.bias_table[h * nb + i] * LOG2E;
 
   auto load_kv = [&](int t, int buf) {
     const int k0 = t * BKV;
-    for (int c = tid; c < BKV * 6; c += 128) {
+    for (int c = tid; c < BKV * 6; c += NTHR) {
       const int r = c / 6, ch = (c % 6) * 8;
       if (k0 + r < klen) {
         cp_async16(&sK[buf][r][ch], kg + (long)(k0 + r) * p.ldk + ch);
@@ -90,8 +104,7 @@ flash48_kernel(const dtts_attention_params p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-  const float LOG2E = 1.4426950408889634f;
-  const float sc = p.scale;
+  const float sc2 = p.scale * LOG2E;
   const int qi0 = q0 + warp * 16 + g;  // query index of c0/c1 rows; +8 for c2/c3
 
   for (int t = 0; t < ntiles; ++t) {
@@ -109,15 +122,15 @@ flash48_kernel(const dtts_attention_params p) {
       for (int ks = 0; ks < 3; ++ks)
         ldsm_x4(qa[ks], &sQ[warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][ks * 16 + ((lane >> 4) & 1) * 8]);
     }
-    float s[8][4];
+    float s[NT][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < NT; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[i][e] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) {
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < NT / 2; ++np) {
         uint32_t kb[4];
         const int mat = lane >> 3;
         ldsm_x4(kb, &sK[buf][np * 16 + (lane & 7) + (mat >> 1) * 8][ks * 16 + (mat & 1) * 8]);
@@ -125,25 +138,40 @@ flash48_kernel(const dtts_attention_params p) {
         mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
       }
     }
-    // scale + bias + key mask, running max
+    // log2-domain scores: scale + bias (+ key mask on the last tile), running max
     const int k0 = t * BKV;
     float mx[2] = {-INFINITY, -INFINITY};
+    // signed distance range of this (warp query rows, key tile): d = key - query
+    const int dmin = k0 - (q0 + warp * 16 + 15), dmax = k0 + BKV - 1 - (q0 + warp * 16);
+    if (nb == 0 || dmin >= half || dmax <= -half) {
+      const float ub = nb == 0 ? 0.f : (dmin >= half ? sBias[2 * half] : sBias[0]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = k0 + nt * 8 + tig * 2 + (e & 1);
-        const int i = qi0 + (e >> 1) * 8;
-        float v = s[nt][e] * sc;
-        if (nb) {
-          int r = j - i;
-          r = r < -p.bias_half ? -p.bias_half : (r > p.bias_half ? p.bias_half : r);
-          v += sBias[r + p.bias_half];
+        for (int e = 0; e < 4; ++e) s[nt][e] = fmaf(s[nt][e], sc2, ub);
+    } else {
+      const int base = k0 + tig * 2 - qi0 + half;   // index for (nt=0, e=0); + nt*8 + (e&1) - (e>>1)*8
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int r = base + nt * 8 + (e & 1) - (e >> 1) * 8;
+          r = min(max(r, 0), 2 * half);
+          s[nt][e] = fmaf(s[nt][e], sc2, sBias[r]);
         }
-        v = j < klen ? v : -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
       }
+    }
+    if (k0 + BKV > klen) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + nt * 8 + tig * 2 + (e & 1) >= klen) s[nt][e] = -INFINITY;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
     float corr[2];
 #pragma unroll
@@ -151,15 +179,15 @@ flash48_kernel(const dtts_attention_params p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float mn = fmaxf(m_run[r], mx[r]);
-      corr[r] = exp2f((m_run[r] - mn) * LOG2E);
+      corr[r] = ex2(m_run[r] - mn);
       m_run[r] = mn;
     }
     float rs[2] = {0.f, 0.f};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f((s[nt][e] - m_run[e >> 1]) * LOG2E);
+        const float pv = ex2(s[nt][e] - m_run[e >> 1]);
         s[nt][e] = pv;
         rs[e >> 1] += pv;
       }
@@ -176,7 +204,7 @@ flash48_kernel(const dtts_attention_params p) {
     }
     // O += P V
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < BKV / 16; ++kk) {
       uint32_t pa[4];
       pa[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
       pa[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
@@ -226,7 +254,7 @@ extern "C" int dtts_attention_f16_flash(const dtts_attention_params* p, void* st
   DTTS_REQUIRE(!p->out_f32 || p->ldo32 % 2 == 0, "attention_f16_flash: ldo32 must be even");
   if (p->n_utt <= 0 || p->max_q_len <= 0) return 0;
   dim3 grid(ceil_div(p->max_q_len, BQ), p->n_heads, p->n_utt);
-  flash48_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*p);
+  flash48_kernel<<<grid, NTHR, 0, (cudaStream_t)stream>>>(*p);
   DTTS_CHECK_LAUNCH("attention_f16_flash");
   return 0;
 }

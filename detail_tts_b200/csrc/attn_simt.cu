@@ -91,6 +91,82 @@ attention_simt_kernel(const dtts_attention_params p) {
   }
 }
 
+// ---- KV-cache decode attention: ONE query per (utterance, head) against its cached keys/values.
+// One warp per (utterance, head), 4 heads per CTA.  Phase 1: 4 lanes share a key (each 3 x float4 of the
+// 48-dim row, 64 B contiguous per key per load), 8 keys per warp iteration, scores to shared memory.
+// Phase 2: 12 lanes x float4 cover a value row (192 B coalesced), two lane groups take even/odd keys and
+// are combined in a fixed order.  fp32 throughout; bit-reproducible.
+constexpr int DEC_WARPS = 4;
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+attention_decode_kernel(const dtts_attention_params p) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * DEC_WARPS + warp, b = blockIdx.y;
+  if (h >= p.n_heads || p.q_len[b] <= 0) return;
+  const int nk = p.k_len[b];
+  if (nk <= 0) return;
+  float* sc = sm + warp * p.max_k_len;
+  const float* q = (const float*)p.q + (long)p.q_off[b] * p.ldq + (long)h * p.head_stride_q;
+  const float* kb = (const float*)p.k + (long)p.k_off[b] * p.ldk + (long)h * p.head_stride_k;
+  const float* vb = (const float*)p.v + (long)p.k_off[b] * p.ldv + (long)h * p.head_stride_v;
+  const int sub = lane & 3, kl = lane >> 2;
+  float4 q4[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    q4[i] = *reinterpret_cast<const float4*>(q + 16 * i + 4 * sub);
+    q4[i].x *= p.scale; q4[i].y *= p.scale; q4[i].z *= p.scale; q4[i].w *= p.scale;
+  }
+  float lmax = -INFINITY;
+  for (int j0 = 0; j0 < nk; j0 += 8) {
+    const int j = j0 + kl;
+    float s = 0.f;
+    if (j < nk) {
+      const float* kj = kb + (long)j * p.ldk + 4 * sub;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kj + 16 * i);
+        s = fmaf(q4[i].x, k4.x, s); s = fmaf(q4[i].y, k4.y, s); s = fmaf(q4[i].z, k4.z, s); s = fmaf(q4[i].w, k4.w, s);
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (j < nk) {
+      if (sub == 0) sc[j] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+  lmax = warp_max(lmax);
+  __syncwarp();
+  float lsum = 0.f;
+  for (int j = lane; j < nk; j += 32) {
+    const float e = expf(sc[j] - lmax);
+    sc[j] = e;
+    lsum += e;
+  }
+  const float inv = 1.0f / warp_sum(lsum);
+  __syncwarp();
+  const int g2 = lane / 12, d4 = lane % 12;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g2 < 2) {
+    for (int j = g2; j < nk; j += 2) {
+      const float pj = sc[j];
+      const float4 v4 = *reinterpret_cast<const float4*>(vb + (long)j * p.ldv + 4 * d4);
+      acc.x = fmaf(pj, v4.x, acc.x); acc.y = fmaf(pj, v4.y, acc.y); acc.z = fmaf(pj, v4.z, acc.z); acc.w = fmaf(pj, v4.w, acc.w);
+    }
+  }
+  const float ox = __shfl_down_sync(0xffffffffu, acc.x, 12), oy = __shfl_down_sync(0xffffffffu, acc.y, 12);
+  const float oz = __shfl_down_sync(0xffffffffu, acc.z, 12), ow = __shfl_down_sync(0xffffffffu, acc.w, 12);
+  if (lane < 12) {
+    const float4 o = make_float4((acc.x + ox) * inv, (acc.y + oy) * inv, (acc.z + oz) * inv, (acc.w + ow) * inv);
+    const long orow = (p.o_off ? p.o_off[b] : p.q_off[b]);
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = o;
+    if (p.out_f16) {
+      __half* hp = (__half*)p.out_f16 + orow * p.ldo16 + h * 48 + 4 * d4;
+      hp[0] = __float2half_rn(o.x); hp[1] = __float2half_rn(o.y); hp[2] = __float2half_rn(o.z); hp[3] = __float2half_rn(o.w);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) {
@@ -107,6 +183,22 @@ extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) 
     cudaFuncSetAttribute(attention_simt_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   }
   DTTS_REQUIRE(p->max_k_len > 0, "attention_f32: max_k_len must be set");
+  // KV-cache decode fast path: one fp32 query per utterance, head_dim 48, no bias
+  if (p->max_q_len == 1 && !p->is_f16 && p->head_dim == 48 && p->bias_mode == DTTS_ATTN_BIAS_NONE && !p->causal &&
+      p->ldq % 4 == 0 && p->ldk % 4 == 0 && p->ldv % 4 == 0 && p->head_stride_q % 4 == 0 && p->head_stride_k % 4 == 0 &&
+      p->head_stride_v % 4 == 0 && ((((uintptr_t)p->q) | ((uintptr_t)p->k) | ((uintptr_t)p->v)) & 15) == 0 &&
+      (!p->out_f32 || (p->ldo32 % 4 == 0 && (((uintptr_t)p->out_f32) & 15) == 0)) &&
+      (size_t)DEC_WARPS * p->max_k_len * sizeof(float) <= 200 * 1024) {
+    static bool dec_attr = false;
+    if (!dec_attr) {
+      cudaFuncSetAttribute(attention_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      dec_attr = true;
+    }
+    dim3 grid(ceil_div(p->n_heads, DEC_WARPS), p->n_utt);
+    attention_decode_kernel<<<grid, DEC_WARPS * 32, (size_t)DEC_WARPS * p->max_k_len * sizeof(float), (cudaStream_t)stream>>>(*p);
+    DTTS_CHECK_LAUNCH("attention_decode");
+    return 0;
+  }
   const int threads = 256;
   const size_t smem = (size_t)(p->head_dim + p->max_k_len + threads) * sizeof(float);
   DTTS_REQUIRE(smem <= (size_t)max_smem, "attention_f32: too many keys for one CTA (%d)", p->max_k_len);

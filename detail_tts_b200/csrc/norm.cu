@@ -113,8 +113,8 @@ groupnorm_kernel(const T* __restrict__ x, int ldx, int C, int cpg, const int* __
 // two-pass (mean, then centred sum of squares) from registers, and the normalised operand is written
 // straight from registers: x is read from HBM exactly once and nothing is staged in shared memory.
 constexpr int GNR_GPC = 2;     // groups per CTA
-constexpr int GNR_MAXR = 16;   // rows per thread
-constexpr int GNR_THREADS = 256;
+constexpr int GNR_MAXR = 11;   // rows per thread (384 threads / 12 float4 columns = 32 rows per sweep -> T <= 352)
+constexpr int GNR_THREADS = 384;
 
 __device__ __forceinline__ float2 block_sum2(float2 v, float2* sh) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -133,7 +133,7 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* sh) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(GNR_THREADS)
+__global__ void __launch_bounds__(GNR_THREADS, 2)
 groupnorm_reg_kernel(const T* __restrict__ x, int ldx, int cpg, const int* __restrict__ utt_off,
                      const int* __restrict__ utt_len, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ film_scale, const float* __restrict__ film_shift, int ld_film,

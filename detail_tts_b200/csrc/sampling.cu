@@ -178,8 +178,9 @@ append_token_kernel(const dtts_append_params p) {
     const int still = unf && (tok != p.stop_token);
     p.unfinished[row] = still;
     if (still && p.n_unfinished) atomicAdd(p.n_unfinished, 1);
-    if (p.kv_row) p.kv_row[row] = row * p.kv_stride + p.kv_pos0 + step;
-    if (p.kv_len) p.kv_len[row] = p.kv_pos0 + step + 1;
+    const int pos0 = p.kv_pos_rows ? p.kv_pos_rows[row] : p.kv_pos0;
+    if (p.kv_row) p.kv_row[row] = row * p.kv_stride + pos0 + step;
+    if (p.kv_len) p.kv_len[row] = pos0 + step + 1;
     tok_s = tok;
   }
   __syncthreads();

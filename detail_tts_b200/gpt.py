@@ -136,6 +136,7 @@ class UnifiedVoice:
         self.max_mel_positions = self.mel_pos.shape[0]
         self.last_latents = None
         self.last_lengths = None
+        self.use_cuda_graph = True      # replay the 74-launch decode step as one CUDA graph
 
     # ------------------------------------------------------------------------------------------
     def _o(self, t):
@@ -331,9 +332,12 @@ class UnifiedVoice:
         def append(nxt):
             lib.call("dtts_append_token", n_rows=B, next=nxt, ids=ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=step,
                      unfinished=unfinished, stop_token=STOP_MEL, tok_emb=self.mel_embedding, pos_emb=self.mel_pos,
-                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL)
+                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
+                     kv_pos_rows=kv_base)
 
         n_gen = 0
+        graph = None
+        use_graph = self.use_cuda_graph
         for s in range(G):
             if do_sample:
                 nxt = (multinomial(probs) if multinomial is not None else torch.multinomial(probs, 1)).reshape(B)
@@ -347,11 +351,17 @@ class UnifiedVoice:
             if (s + 1) % sync_every == 0 or B == 1:
                 if int(unfinished.sum()) == 0:
                     break
-            # KV rows of this step: position P_b + 1 + s of utterance b
-            torch.add(kv_base, s, out=kv_len)
-            torch.add(k_off, kv_len, out=kv_row)
-            kv_len.add_(1)
-            plan.run()
+            # (append_token also set this step's KV row/length: position P_b + 1 + s of utterance b)
+            if graph is not None:
+                graph.replay()
+            else:
+                plan.run()          # first step eagerly (one-time attribute/tensor-map setup), then capture
+                if use_graph and G > 2:
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph):
+                        plan.run()
+                    # the capture does not execute: nothing to undo
             latents[:, s + 1].copy_(hn)
         codes = ids[:, n_ids0:n_ids0 + n_gen].clone()
         # trim trailing all-pad columns produced between host checks
@@ -361,6 +371,7 @@ class UnifiedVoice:
             n_keep = int(done_at.max())
             codes = codes[:, :n_keep]
         self.last_latents = latents
+        self.last_plan = plan
         return codes
 
     inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528

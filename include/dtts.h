@@ -144,6 +144,7 @@ typedef struct {
   float* x_out; int ldx;
   int* kv_row; int kv_stride;    /* optional [n_rows]: kv_row[b] = b*kv_stride + kv_pos0 + step (next KV/out row) */
   int kv_pos0; int* kv_len;      /* optional [n_rows]: kv_len[b] = kv_pos0 + step + 1 (keys visible next step) */
+  const int* kv_pos_rows;        /* optional [n_rows]: per-row base position used instead of kv_pos0 (varlen prefixes) */
 } dtts_append_params;
 /* HF _sample bookkeeping (generation/utils.py:2797-2805) + next-token embedding
  * mel_embedding[id] + mel_pos_embedding[pos] (gpt/model.py:145-148). */
