@@ -262,35 +262,48 @@ def main():
         torch.cuda.synchronize()
         return wav_h
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed_pair(fn_a, fn_b, steps, warmup, sampler=None):
+        """Time `steps` iterations of fn_a and of fn_b INTERLEAVED (a, b, a, b, ...) so both see the same clocks /
+        power state; device time by CUDA events, max over ranks.  Returns (ms_a, ms_b, launches_a, clocks)."""
         for _ in range(warmup):
-            fn()
+            fn_a()
+        fn_b()
         barrier()
         if sampler:
             sampler.start()
-        l0 = lib.launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ea, eb = [], []
+        la = 0
         for _ in range(steps):
-            fn()
-        e1.record()
+            barrier()
+            l0 = lib.launches()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            fn_a()
+            e1.record()
+            la += lib.launches() - l0
+            barrier()
+            e1b = torch.cuda.Event(enable_timing=True)
+            e1b.record()
+            fn_b()
+            e2.record()
+            ea.append((e0, e1))
+            eb.append((e1b, e2))
         barrier()
-        ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
-        n_launch = lib.launches() - l0
-        t = torch.tensor([ms, float(n_launch)], device=dev, dtype=torch.float64)
+        ms_a = sum(a.elapsed_time(b) for a, b in ea)
+        ms_b = sum(a.elapsed_time(b) for a, b in eb)
+        t = torch.tensor([ms_a, ms_b, float(la)], device=dev, dtype=torch.float64)
         if world > 1:
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             tsum = t.clone()
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            return float(tmax[0]), int(tsum[1]), clocks
-        return float(t[0]), int(t[1]), clocks
+            return float(tmax[0]), float(tmax[1]), int(tsum[2]), clocks
+        return float(t[0]), float(t[1]), int(t[2]), clocks
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    ms, ms_e2e, launches, clocks = timed_pair(step_resident, step_e2e, args.steps, args.warmup, sampler)
     value = audio_s_total * args.steps / (ms * 1e-3)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
     e2e_value = audio_s_total * args.steps / (ms_e2e * 1e-3)
 
     roof = None

@@ -159,7 +159,15 @@ attention_decode_kernel(const dtts_attention_params p) {
   if (lane < 12) {
     const float4 o = make_float4((acc.x + ox) * inv, (acc.y + oy) * inv, (acc.z + oz) * inv, (acc.w + ow) * inv);
     const long orow = (p.o_off ? p.o_off[b] : p.q_off[b]);
-    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = o;
+    if (p.out_lo) {   // tf32 operand split for the projection GEMM (dtts_gemm_tf32x3)
+      float4 hi, lo;
+      hi.x = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u); lo.x = o.x - hi.x;
+      hi.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u); lo.y = o.y - hi.y;
+      hi.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); lo.z = o.z - hi.z;
+      hi.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u); lo.w = o.w - hi.w;
+      *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = hi;
+      *reinterpret_cast<float4*>(p.out_lo + orow * p.ldo_lo + h * 48 + 4 * d4) = lo;
+    } else if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = o;
     if (p.out_f16) {
       __half* hp = (__half*)p.out_f16 + orow * p.ldo16 + h * 48 + 4 * d4;
       hp[0] = __float2half_rn(o.x); hp[1] = __float2half_rn(o.y); hp[2] = __float2half_rn(o.z); hp[3] = __float2half_rn(o.w);
@@ -199,6 +207,7 @@ extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) 
     DTTS_CHECK_LAUNCH("attention_decode");
     return 0;
   }
+  DTTS_REQUIRE(!p->out_lo, "attention_f32: out_lo (tf32 split) is only produced by the fp32 KV-cache decode path");
   const int threads = 256;
   const size_t smem = (size_t)(p->head_dim + p->max_k_len + threads) * sizeof(float);
   DTTS_REQUIRE(smem <= (size_t)max_smem, "attention_f32: too many keys for one CTA (%d)", p->max_k_len);

@@ -323,6 +323,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_logits_params); SZ(dtts_append_params); SZ(dtts_pstep_params); SZ(dtts_bct2rows_params);
   SZ(dtts_rows2bct_params); SZ(dtts_eltwise_params); SZ(dtts_embed_params); SZ(dtts_repeat_rows_params);
   SZ(dtts_mean_rows_params); SZ(dtts_tsemb_params); SZ(dtts_couple_params); SZ(dtts_zp_params);
-  SZ(dtts_rowutt_params);
+  SZ(dtts_rowutt_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
   return -1;
 }

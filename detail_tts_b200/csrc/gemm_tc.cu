@@ -27,10 +27,13 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA(+TMEM 
 constexpr int EPI_LD = 36;        // padded fp32 row of the per-warp 32x32 transpose staging tile
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
 
-template <int BN>
+// TF32 = true: 3xTF32 fp32-class GEMM.  Operands are fp32 split on the host side of the ABI into a
+// tf32-exact high part and a low part (x = hi + lo); a stage holds {A_hi, A_lo, W_hi, W_lo} tiles (32 fp32 =
+// 128 B rows, same swizzle span) and the MMA warp issues hi*hi + lo*hi + hi*lo (kind::tf32, K=8 per MMA).
+template <int BN, bool TF32 = false>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_BYTES = BN * BK * 2;   // BN rows x 128 B, for fp16 (64 el) and tf32 (32 el) alike
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = 2 * BN;
@@ -107,6 +110,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -124,11 +135,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int BN>
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride, const int debug) {
-  using C = Cfg<BN>;
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
+               EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride,
+               const int kb_per_split, const long split_stride, const int debug) {
+  using C = Cfg<BN, TF32>;
+  constexpr int BKE = TF32 ? 32 : 64;   // elements per 128-byte K block
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries of the SHARED address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -145,8 +159,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (epi.M + BM - 1) / BM;
   const int n_tiles = (epi.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (K + BK - 1) / BK;
+  // split-K: blockIdx.y owns K blocks [kb0, kb0 + k_blocks) and writes a raw partial tile set at
+  // out_f32 + blockIdx.y * split_stride (the host strips bias/act/residual from `epi` in that mode)
+  const int k_blocks_all = (K + BKE - 1) / BKE;
+  const int kb0 = blockIdx.y * kb_per_split;
+  const int k_blocks = min(kb_per_split, k_blocks_all - kb0);
   const int k_iters = taps * k_blocks;
+  if (epi.out_f32) epi.out_f32 += (long)blockIdx.y * split_stride;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -168,6 +187,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+      if (TF32) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
+      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BM;
@@ -179,8 +202,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0 + tap_shift0 + tap * tap_stride);
-          tma_load_2d(sb, &tmW, &full[stage], kb * BK, tap * epi.N + n0);
+          tma_load_2d(sa, &tmA, &full[stage], (kb0 + kb) * BKE, m0 + tap_shift0 + tap * tap_stride);
+          tma_load_2d(sb, &tmW, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
+          if (TF32) {
+            tma_load_2d(sb + C::B_BYTES, &tmA2, &full[stage], (kb0 + kb) * BKE, m0 + tap_shift0 + tap * tap_stride);
+            tma_load_2d(sb + C::B_BYTES + A_BYTES, &tmW2, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -188,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN) | (TF32 ? ((2u << 7) | (2u << 10)) : 0u);   // a/b format: F16 = 0, TF32 = 2
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -200,11 +227,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          if (!TF32) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_desc(sa + k * 32);
-            const uint64_t db = make_desc(sb + k * 32);
-            umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {   // 4 x (K=16 fp16 = 32 B)
+              const uint64_t da = make_desc(sa + k * 32);
+              const uint64_t db = make_desc(sb + k * 32);
+              umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint32_t sa2 = sb + C::B_BYTES, sb2 = sa2 + A_BYTES;
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {   // hi*hi, lo*hi, hi*lo -- small terms last is not needed: fp32 accumulate
+              const uint32_t xa = seg == 1 ? sa2 : sa, xb = seg == 2 ? sb2 : sb;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {   // 4 x (K=8 tf32 = 32 B)
+                umma_tf32(d_tmem, make_desc(xa + k * 32), make_desc(xb + k * 32), idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
+              }
+            }
           }
           tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -354,25 +393,26 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows;
+  const void* ptr; int rows, cols, ld, box_rows, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.ptr;
     h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box_rows;
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box_rows; h = h * 1000003u ^ (size_t)k.esize;
     return h;
   }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// 2D fp16 tensor map over a row-major [rows, cols] matrix (ld elements), box [box_rows, 64], 128B swizzle.
-int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, rows, cols, ld, box_rows};
+// 2D tensor map (fp16: esize 2, fp32: esize 4) over a row-major [rows, cols] matrix (ld elements),
+// box [box_rows, 128 bytes], 128B swizzle.
+int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int esize = 2) {
+  MapKey key{ptr, rows, cols, ld, box_rows, esize};
   {
     std::lock_guard<std::mutex> g(g_maps_mu);
     auto it = g_maps.find(key);
@@ -381,10 +421,10 @@ int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorM
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) DTTS_FAIL(-4, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -398,39 +438,55 @@ int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorM
 int g_sm_count = 0;
 int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
-template <int BN>
+template <int BN, bool TF32>
 int launch(const dtts_gemm_params* p, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap ma, mw;
-  int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma);
+  const int es = TF32 ? 4 : 2;
+  CUtensorMap ma, mw, ma2, mw2;
+  int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma, es);
   if (rc) return rc;
-  rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN, &mw);
+  rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN, &mw, es);
   if (rc) return rc;
+  ma2 = ma; mw2 = mw;
+  if (TF32) {
+    rc = get_map(p->A_lo, p->M, p->K, p->lda, BM, &ma2, es);
+    if (rc) return rc;
+    rc = get_map(p->W_lo, p->taps * p->N, p->K, p->ldw, BN, &mw2, es);
+    if (rc) return rc;
+  }
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, BN);
-  const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+  const int kb_all = ceil_div(p->K, TF32 ? 32 : 64);
+  int splits = TF32 && p->split_k > 1 ? p->split_k : 1;
+  if (splits > kb_all) splits = kb_all;
+  const int kb_per = ceil_div(kb_all, splits);
+  splits = ceil_div(kb_all, kb_per);
   EpiParams e = make_epi(p);
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride, g_debug);
+  if (TF32 && p->split_k > 1) {   // raw partials: the reduce kernel applies bias / activation / residual
+    e.bias = nullptr; e.bias_utt = nullptr; e.res = nullptr; e.out_f16 = nullptr; e.out_row_map = nullptr;
+    e.act = DTTS_ACT_NONE; e.act16 = DTTS_ACT_NONE; e.alpha = 1.0f; e.accumulate = 0; e.row_utt = nullptr;
+  }
+  dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
+  gemm_tc_kernel<BN, TF32><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+                                                                      kb_per, (long)p->split_stride, g_debug);
   DTTS_CHECK_LAUNCH("gemm_tc");
   return 0;
 }
 
-}  // namespace
-
-extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
-  DTTS_REQUIRE(p && p->A && p->W, "gemm_f16_tc: null operand");
-  DTTS_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0 && p->taps >= 1, "gemm_f16_tc: bad shape M=%d N=%d K=%d taps=%d", p->M, p->N, p->K, p->taps);
-  DTTS_REQUIRE((p->lda % 8) == 0 && (p->ldw % 8) == 0, "gemm_f16_tc: lda/ldw must be multiples of 8 (16-byte TMA strides)");
-  DTTS_REQUIRE((((uintptr_t)p->A) & 15) == 0 && (((uintptr_t)p->W) & 15) == 0, "gemm_f16_tc: operands must be 16-byte aligned");
-  DTTS_REQUIRE(p->lda >= p->K && p->ldw >= p->K, "gemm_f16_tc: leading dimension smaller than K");
-  DTTS_REQUIRE(!(p->bias_utt && !p->row_utt), "gemm_f16_tc: bias_utt requires row_utt");
-  DTTS_REQUIRE(p->out_f32 || p->out_f16, "gemm_f16_tc: no output");
-  DTTS_REQUIRE(!(p->act >= DTTS_ACT_PAIR_TANH_SIGMOID && (p->N & 1)), "gemm_f16_tc: pair activation needs even N");
+int common_checks(const dtts_gemm_params* p, const char* who, int ld_mult) {
+  DTTS_REQUIRE(p && p->A && p->W, "%s: null operand", who);
+  DTTS_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0 && p->taps >= 1, "%s: bad shape M=%d N=%d K=%d taps=%d", who, p->M, p->N, p->K, p->taps);
+  DTTS_REQUIRE((p->lda % ld_mult) == 0 && (p->ldw % ld_mult) == 0, "%s: lda/ldw must keep 16-byte TMA strides", who);
+  DTTS_REQUIRE((((uintptr_t)p->A) & 15) == 0 && (((uintptr_t)p->W) & 15) == 0, "%s: operands must be 16-byte aligned", who);
+  DTTS_REQUIRE(p->lda >= p->K && p->ldw >= p->K, "%s: leading dimension smaller than K", who);
+  DTTS_REQUIRE(!(p->bias_utt && !p->row_utt), "%s: bias_utt requires row_utt", who);
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "%s: no output", who);
+  DTTS_REQUIRE(!(p->act >= DTTS_ACT_PAIR_TANH_SIGMOID && (p->N & 1)), "%s: pair activation needs even N", who);
   if (g_debug < 0) {
     const char* d = getenv("DTTS_GEMM_DEBUG");
     g_debug = d ? atoi(d) : 0;
@@ -439,12 +495,31 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) DTTS_FAIL(-6, "gemm_f16_tc: no CUDA device");
+    if (g_sm_count <= 0) DTTS_FAIL(-6, "%s: no CUDA device", who);
   }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
+  int rc = common_checks(p, "gemm_f16_tc", 8);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->N;
-  if (N % 192 == 0) return launch<192>(p, st);
-  if (N > 64) return launch<128>(p, st);
-  if (N > 32) return launch<64>(p, st);
-  return launch<32>(p, st);
+  if (N % 192 == 0) return launch<192, false>(p, st);
+  if (N > 64) return launch<128, false>(p, st);
+  if (N > 32) return launch<64, false>(p, st);
+  return launch<32, false>(p, st);
+}
+
+extern "C" int dtts_gemm_tf32x3(const dtts_gemm_params* p, void* stream) {
+  int rc = common_checks(p, "gemm_tf32x3", 4);
+  if (rc) return rc;
+  DTTS_REQUIRE(p->A_lo && p->W_lo, "gemm_tf32x3: missing low-part operands");
+  DTTS_REQUIRE((((uintptr_t)p->A_lo) & 15) == 0 && (((uintptr_t)p->W_lo) & 15) == 0, "gemm_tf32x3: low parts must be 16-byte aligned");
+  DTTS_REQUIRE(p->split_k <= 1 || (p->out_f32 && p->split_stride >= (int64_t)p->M * p->ldo32), "gemm_tf32x3: split-K needs an fp32 partial buffer of split_k x M x ldo32");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->M > 256 && p->N >= 128) return launch<128, true>(p, st);
+  return launch<64, true>(p, st);
 }

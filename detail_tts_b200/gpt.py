@@ -105,29 +105,41 @@ class MelStyleEncoder:
 class _Trunk:
     """HF GPT2Model weights (wpe nulled: gpt/model.py:12-13,233-234) in GEMM form."""
 
-    def __init__(self, W, dtype, device, p="gpt.gpt."):
+    def __init__(self, W, dtype, device, p="gpt.gpt.", tf32x3=False):
         f32 = lambda k: W[k].to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        if tf32x3:
+            pk = lambda w, b: pack.pack_linear_tf32x3(W[w].t(), W[b], device)  # noqa: E731  (HF Conv1D is [in,out])
+        else:
+            pk = lambda w, b: pack.pack_hf_conv1d(W[w], W[b], dtype, device)  # noqa: E731
         self.layers = []
         for l in range(N_LAYERS):
             q = p + f"h.{l}."
             self.layers.append(dict(
                 ln1=(f32(q + "ln_1.weight"), f32(q + "ln_1.bias")),
                 ln2=(f32(q + "ln_2.weight"), f32(q + "ln_2.bias")),
-                attn=pack.pack_hf_conv1d(W[q + "attn.c_attn.weight"], W[q + "attn.c_attn.bias"], dtype, device),
-                proj=pack.pack_hf_conv1d(W[q + "attn.c_proj.weight"], W[q + "attn.c_proj.bias"], dtype, device),
-                fc=pack.pack_hf_conv1d(W[q + "mlp.c_fc.weight"], W[q + "mlp.c_fc.bias"], dtype, device),
-                out=pack.pack_hf_conv1d(W[q + "mlp.c_proj.weight"], W[q + "mlp.c_proj.bias"], dtype, device)))
+                attn=pk(q + "attn.c_attn.weight", q + "attn.c_attn.bias"),
+                proj=pk(q + "attn.c_proj.weight", q + "attn.c_proj.bias"),
+                fc=pk(q + "mlp.c_fc.weight", q + "mlp.c_fc.bias"),
+                out=pk(q + "mlp.c_proj.weight", q + "mlp.c_proj.bias")))
         self.ln_f = (f32(p + "ln_f.weight"), f32(p + "ln_f.bias"))
 
 
 class UnifiedVoice:
-    def __init__(self, W, device="cuda", dtype=torch.float32):
-        self.device, self.dtype = torch.device(device), dtype
+    def __init__(self, W, device="cuda", dtype="tf32x3"):
+        """dtype: "tf32x3" (default: fp32-class 3xTF32 GEMMs on tcgen05 tensor cores), torch.float32 (exact fp32
+        FMA on CUDA cores) or torch.float16 (plain fp16 tensor-core GEMMs; not token-exact)."""
+        self.device = torch.device(device)
+        self.tf32x3 = dtype == "tf32x3"
+        self.dtype = dtype = torch.float32 if self.tf32x3 else dtype
         dev = self.device
         f32 = lambda k: W[k].to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
-        self.trunk = _Trunk(W, dtype, dev)
+        self.trunk = _Trunk(W, dtype, dev, tf32x3=self.tf32x3)
         self.final_norm = (f32("gpt.final_norm.weight"), f32("gpt.final_norm.bias"))
-        self.mel_head = pack.pack_linear(W["gpt.mel_head.weight"], W["gpt.mel_head.bias"], dtype, dev)
+        if self.tf32x3:
+            self.mel_head = pack.pack_linear_tf32x3(W["gpt.mel_head.weight"], W["gpt.mel_head.bias"], dev, n_pad=4)
+        else:
+            self.mel_head = pack.pack_linear(W["gpt.mel_head.weight"], W["gpt.mel_head.bias"], dtype, dev)
+        self.n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self.mel_embedding = f32("gpt.mel_embedding.weight")
         self.mel_pos = f32("gpt.mel_pos_embedding.emb.weight")
         self.text_embedding = f32("gpt.text_embedding.weight")
@@ -201,6 +213,8 @@ class UnifiedVoice:
                 rm += [b * arena_stride + i for i in range(seq_len[b])]
             row_map = _i32(rm, dev)
             qoff = _i32([b * arena_stride for b in range(B)], dev)
+        if self.tf32x3:
+            return self._trunk_rows_tf32(x, so, sl, max_len, arena, row_map, qoff if arena is not None else so)
         h = torch.empty(M, D_MODEL, dtype=dt, device=dev)
         a = torch.empty(M, D_MODEL, dtype=dt, device=dev)
         u = torch.empty(M, 4 * D_MODEL, dtype=dt, device=dev)
@@ -223,6 +237,30 @@ class UnifiedVoice:
             ops.gemm(u, ly["out"], res=x, out32=x)
         y = torch.empty(M, D_MODEL, dtype=torch.float32, device=dev)
         ops.layernorm(x, *self.trunk.ln_f, out32=y)
+        return y
+
+    def _trunk_rows_tf32(self, x, so, sl, max_len, arena, row_map, q_off):
+        """_trunk_rows on the 3xTF32 tensor-core GEMM (all positions; normal fused epilogues, no split-K)."""
+        dev = self.device
+        M = x.shape[0]
+        e = lambda c: torch.empty(M, c, dtype=torch.float32, device=dev)  # noqa: E731
+        hh, hl, a32, ah, al, u32 = e(D_MODEL), e(D_MODEL), e(D_MODEL), e(D_MODEL), e(D_MODEL), e(4 * D_MODEL)
+        uh, ul = e(4 * D_MODEL), e(4 * D_MODEL)
+        qkv_c = None if arena is not None else e(3 * D_MODEL)
+        for l, ly in enumerate(self.trunk.layers):
+            ops.splitk_reduce(None, 0, M, D_MODEL, res=x, ln=ly["ln1"], y_hi=hh, y_lo=hl)
+            qkv = arena[l] if arena is not None else qkv_c
+            ops.gemm_tf32x3(hh, hl, ly["attn"], qkv, out_row_map=row_map)
+            ops.attention(qkv, qkv[:, D_MODEL:], qkv[:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, q_off, sl, q_off, sl,
+                          max_len, max_len, HEAD_DIM ** -0.5, causal=True, o_off=so, out32=a32)
+            ops.split_tf32(a32, ah, al)
+            ops.gemm_tf32x3(ah, al, ly["proj"], x, res=x)
+            ops.splitk_reduce(None, 0, M, D_MODEL, res=x, ln=ly["ln2"], y_hi=hh, y_lo=hl)
+            ops.gemm_tf32x3(hh, hl, ly["fc"], u32, act=ops.ACT_GELU_NEW)
+            ops.split_tf32(u32, uh, ul)
+            ops.gemm_tf32x3(uh, ul, ly["out"], x, res=x)
+        y = e(D_MODEL)
+        ops.splitk_reduce(None, 0, M, D_MODEL, res=x, ln=self.trunk.ln_f, y32=y)
         return y
 
     def get_conditioning(self, speech_conditioning_latent, cond_lengths):
@@ -285,7 +323,19 @@ class UnifiedVoice:
         adt = torch.empty(B, D_MODEL, dtype=dt, device=dev)
         udt = torch.empty(B, 4 * D_MODEL, dtype=dt, device=dev)
         t32 = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
-        logits = torch.empty(B, VOCAB, dtype=torch.float32, device=dev)
+        if self.tf32x3:
+            e32 = lambda c: torch.empty(B, c, dtype=torch.float32, device=dev)  # noqa: E731
+            xh, xl, ah, al, uh, ul = e32(D_MODEL), e32(D_MODEL), e32(D_MODEL), e32(D_MODEL), e32(4 * D_MODEL), e32(4 * D_MODEL)
+
+            def splits(pw):      # fill the SMs: (N/64 column tiles) x split_k CTAs
+                tiles = (pw.N + 63) // 64
+                return ops.n_splits_for(pw.K, max(1, round(self.n_sm / tiles)))
+            ly0 = self.trunk.layers[0]
+            S = {k: splits(ly0[k]) for k in ("attn", "proj", "fc", "out")}
+            ws = torch.empty(max(S[k] * B * ly0[k].N for k in S), dtype=torch.float32, device=dev)
+            wsv = {k: ws[:S[k] * B * ly0[k].N].view(S[k], B, ly0[k].N) for k in S}
+        LDL = self.mel_head.N if self.tf32x3 else VOCAB      # logits row pitch (head padded to a multiple of 4)
+        logits = torch.empty(B, LDL, dtype=torch.float32, device=dev)
         probs = torch.zeros(B, VOCAB, dtype=torch.float32, device=dev)
         argmax = torch.zeros(B, dtype=torch.long, device=dev)
         unfinished = torch.ones(B, dtype=torch.int32, device=dev)
@@ -303,9 +353,13 @@ class UnifiedVoice:
 
         def head(src_rows_x, M, first):
             """ln_f'd hidden -> final_norm -> logits -> processed probs/argmax"""
-            ops.layernorm(src_rows_x, *self.final_norm, out32=hn, **({"out16": hdt} if dt == torch.float16 else {}))
-            ops.gemm(hdt if dt == torch.float16 else hn, self.mel_head, out32=logits)
-            lib.call("dtts_process_logits", logits=logits, ldl=VOCAB, n_rows=B, vocab=VOCAB, ids=ids, ld_ids=ld_ids,
+            if self.tf32x3:
+                ops.splitk_reduce(None, 0, B, D_MODEL, res=src_rows_x, ln=self.final_norm, y32=hn, y_hi=xh, y_lo=xl)
+                ops.gemm_tf32x3(xh, xl, self.mel_head, logits)
+            else:
+                ops.layernorm(src_rows_x, *self.final_norm, out32=hn, **({"out16": hdt} if dt == torch.float16 else {}))
+                ops.gemm(hdt if dt == torch.float16 else hn, self.mel_head, out32=logits)
+            lib.call("dtts_process_logits", logits=logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=ids, ld_ids=ld_ids,
                      n_ids=n_ids0, step_dev=step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
                      do_sample=int(do_sample), suppress_token=suppress_token, probs=probs, ldp=VOCAB, argmax=argmax)
 
@@ -317,7 +371,30 @@ class UnifiedVoice:
         kv_base = _i32([P[b] + 1 for b in range(B)], dev)        # KV position of generated token 0
 
         with lib.record() as plan:
-            for l, ly in enumerate(self.trunk.layers):
+            if self.tf32x3:
+                L_ = self.trunk.layers
+                ops.splitk_reduce(None, 0, B, D_MODEL, res=xs, ln=L_[0]["ln1"], y_hi=xh, y_lo=xl)
+                for l, ly in enumerate(L_):
+                    ops.gemm_tf32x3(xh, xl, ly["attn"], wsv["attn"], split_k=S["attn"])
+                    ops.splitk_reduce(wsv["attn"], S["attn"], B, 3 * D_MODEL, bias=ly["attn"].bias, out32=arena[l],
+                                      out_row_map=kv_row)
+                    ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
+                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=ah, out_lo=al)
+                    ops.gemm_tf32x3(ah, al, ly["proj"], wsv["proj"], split_k=S["proj"])
+                    ops.splitk_reduce(wsv["proj"], S["proj"], B, D_MODEL, bias=ly["proj"].bias, res=xs, out32=xs,
+                                      ln=ly["ln2"], y_hi=xh, y_lo=xl)
+                    ops.gemm_tf32x3(xh, xl, ly["fc"], wsv["fc"], split_k=S["fc"])
+                    ops.splitk_reduce(wsv["fc"], S["fc"], B, 4 * D_MODEL, bias=ly["fc"].bias, act=ops.ACT_GELU_NEW,
+                                      y_hi=uh, y_lo=ul)
+                    ops.gemm_tf32x3(uh, ul, ly["out"], wsv["out"], split_k=S["out"])
+                    if l + 1 < len(L_):
+                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
+                                          ln=L_[l + 1]["ln1"], y_hi=xh, y_lo=xl)
+                    else:
+                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
+                                          ln=self.trunk.ln_f, y32=t32)
+                head(t32, B, False)
+            for l, ly in enumerate([] if self.tf32x3 else self.trunk.layers):
                 ops.layernorm(xs, *ly["ln1"], **self._o(hdt))
                 ops.gemm(hdt, ly["attn"], out_row_map=kv_row, **self._o(arena[l]))
                 ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
@@ -326,8 +403,9 @@ class UnifiedVoice:
                 ops.layernorm(xs, *ly["ln2"], **self._o(hdt))
                 ops.gemm(hdt, ly["fc"], act=ops.ACT_GELU_NEW, **self._o(udt))
                 ops.gemm(udt, ly["out"], res=xs, out32=xs)
-            ops.layernorm(xs, *self.trunk.ln_f, out32=t32)
-            head(t32, B, False)
+            if not self.tf32x3:
+                ops.layernorm(xs, *self.trunk.ln_f, out32=t32)
+                head(t32, B, False)
 
         def append(nxt):
             lib.call("dtts_append_token", n_rows=B, next=nxt, ids=ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=step,

@@ -17,7 +17,7 @@ from .gpt import STOP_MEL, UnifiedVoice
 
 
 class SynthesizerTrn:
-    def __init__(self, state_dict, device="cuda", gpt_dtype=torch.float32, diffusion_steps=50):
+    def __init__(self, state_dict, device="cuda", gpt_dtype="tf32x3", diffusion_steps=50):
         if not torch.cuda.is_available():
             raise RuntimeError("detail_tts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device)

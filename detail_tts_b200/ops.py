@@ -18,12 +18,54 @@ def _ld(t):
 
 
 class PackedConv:
-    """A conv/linear weight in GEMM form: W [taps*N, K] (tap-major, K contiguous), bias [N]."""
-    __slots__ = ("w", "bias", "N", "K", "taps", "shift0", "stride")
+    """A conv/linear weight in GEMM form: W [taps*N, K] (tap-major, K contiguous), bias [N].
+    `w_lo` (3xTF32 mode): w holds the tf32-exact high part, w_lo the low part."""
+    __slots__ = ("w", "bias", "N", "K", "taps", "shift0", "stride", "w_lo")
 
-    def __init__(self, w, bias, N, K, taps=1, shift0=0, stride=1):
+    def __init__(self, w, bias, N, K, taps=1, shift0=0, stride=1, w_lo=None):
         self.w, self.bias, self.N, self.K = w, bias, N, K
         self.taps, self.shift0, self.stride = taps, shift0, stride
+        self.w_lo = w_lo
+
+
+def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None, split_k=1, bias=True):
+    """fp32-class GEMM on tcgen05 (3xTF32).  split_k > 1: out32 is a partial buffer [split_k, M, N]
+    (finish with splitk_reduce); otherwise the normal fused epilogue."""
+    M = A_hi.shape[0]
+    if split_k > 1:
+        assert out32.dim() == 3 and out32.is_contiguous()
+        _lib.lib().call("dtts_gemm_tf32x3", A=A_hi, A_lo=A_lo, W=pw.w, W_lo=pw.w_lo, M=M, N=pw.N, K=pw.K, lda=_ld(A_hi),
+                        ldw=_ld(pw.w), taps=1, tap_shift0=0, tap_stride=1, out_f32=out32, ldo32=out32.shape[2],
+                        act=ACT_NONE, alpha=1.0, split_k=split_k, split_stride=out32.shape[1] * out32.shape[2])
+        return
+    _lib.lib().call("dtts_gemm_tf32x3", A=A_hi, A_lo=A_lo, W=pw.w, W_lo=pw.w_lo, M=M, N=pw.N, K=pw.K, lda=_ld(A_hi),
+                    ldw=_ld(pw.w), taps=1, tap_shift0=0, tap_stride=1, bias=pw.bias if bias else None,
+                    out_row_map=out_row_map, res=res, ldr=_ld(res) if res is not None else 0, out_f32=out32,
+                    ldo32=_ld(out32), act=act, alpha=1.0, split_k=1)
+
+
+def n_splits_for(K, split_k):
+    """The number of K splits dtts_gemm_tf32x3 actually uses for a requested split_k (32-wide K blocks)."""
+    kb = (K + 31) // 32
+    s = max(1, min(split_k, kb))
+    per = (kb + s - 1) // s
+    return (kb + per - 1) // per
+
+
+def splitk_reduce(ws, n_splits, M, N, bias=None, act=ACT_NONE, res=None, out32=None, out_row_map=None, ln=None,
+                  y32=None, y_hi=None, y_lo=None):
+    """v = act(sum_s ws[s] + bias) + res -> out32[row map]; y = LayerNorm(v) (or v) -> y32 / (y_hi, y_lo)."""
+    _lib.lib().call("dtts_splitk_reduce", ws=ws if n_splits else None,
+                    split_stride=ws.shape[1] * ws.shape[2] if n_splits else 0, n_splits=n_splits,
+                    ld_ws=ws.shape[2] if n_splits else 0, M=M, N=N, bias=bias, act=act, res=res,
+                    ldr=_ld(res) if res is not None else 0, out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+                    out_row_map=out_row_map, ln_gamma=ln[0] if ln else None, ln_beta=ln[1] if ln else None, ln_eps=1e-5,
+                    y_f32=y32, ldy=_ld(y32) if y32 is not None else 0, y_hi=y_hi, y_lo=y_lo,
+                    ld_hl=_ld(y_hi) if y_hi is not None else 0)
+
+
+def split_tf32(x, hi, lo):
+    _lib.lib().call("dtts_split_tf32", x=x, ldx=_ld(x), M=x.shape[0], C=x.shape[1], hi=hi, lo=lo, ld=_ld(hi))
 
 
 def gemm(A, pw, out32=None, out16=None, res=None, act=ACT_NONE, act_param=0.0, act16=ACT_NONE,
@@ -66,7 +108,7 @@ def layernorm(x, gamma, beta, out32=None, out16=None, res=None, M=None, eps=1e-5
 
 def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max_k, scale, out32=None, out16=None,
               head_stride=None, causal=False, causal_offset=None, bias_table=None, bias_half=0, rel_k=None,
-              rel_v=None, window=0, o_off=None, flash=False):
+              rel_v=None, window=0, o_off=None, flash=False, out_lo=None):
     L = _lib.lib()
     hs = head_dim if head_stride is None else head_stride
     mode = BIAS_RELPOS_TABLE if bias_table is not None else (BIAS_WINDOW_REL if rel_k is not None else BIAS_NONE)
@@ -77,7 +119,8 @@ def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max
            causal=int(causal), causal_offset=causal_offset, scale=scale, bias_mode=mode, bias_table=bias_table,
            bias_half=bias_half, rel_k=rel_k, rel_v=rel_v, window=window,
            out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
-           out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, o_off=o_off)
+           out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, o_off=o_off,
+           out_lo=out_lo, ldo_lo=_ld(out_lo) if out_lo is not None else 0)
 
 
 def bct_to_rows(src, lay, dst32=None, dst16=None, scale=1.0, shift=0.0):

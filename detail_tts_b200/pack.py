@@ -141,3 +141,17 @@ def interleave_halves(w, b):
     H = w.shape[0] // 2
     idx = torch.stack([torch.arange(H), torch.arange(H) + H], 1).reshape(-1)
     return w[idx], (None if b is None else b[idx]), idx
+
+
+def split_tf32_host(w):
+    """w (fp32) -> (hi, lo): hi keeps sign/exponent/10 mantissa bits (tf32-exact), lo = w - hi (exact)."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def pack_linear_tf32x3(w, b, device, n_pad=1):
+    """nn.Linear weight [N, K] -> PackedConv for dtts_gemm_tf32x3 (hi/lo fp32 pair)."""
+    pw = pack_linear(w, b, torch.float32, device, n_pad=n_pad, k_pad=4)
+    hi, lo = split_tf32_host(pw.w)
+    pw.w, pw.w_lo = hi.contiguous(), lo.contiguous()
+    return pw

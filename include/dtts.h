@@ -56,6 +56,11 @@ typedef struct {
   float act_param, act16_param;
   float alpha;            /* out = alpha*(act(acc+bias)+res) (+ out_old if accumulate) */
   int accumulate;
+  /* dtts_gemm_tf32x3 only: */
+  const void* A_lo;       /* fp32 low parts: A = A_hi + A_lo with A_hi tf32-exact (dtts_split_tf32) */
+  const void* W_lo;       /* same for W */
+  int split_k;            /* > 1: K is split over split_k CTAs per tile; raw partial sums are written to        */
+  int64_t split_stride;   /*   out_f32 + s*split_stride (elements) and bias/act/res/out_f16 are ignored          */
 } dtts_gemm_params;
 
 /* D = epilogue(sum_taps A[m+shift_t,:] . W_t[n,:]) on tcgen05 tensor cores (fp16 operands, fp32
@@ -66,6 +71,12 @@ typedef struct {
 int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream);
 /* Same contract in exact fp32 FMA arithmetic on CUDA cores (token-exact GPT path, small shapes). */
 int dtts_gemm_f32(const dtts_gemm_params* p, void* stream);
+/* Same contract at fp32-class accuracy on tcgen05 tensor cores: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32
+ * accumulation in TMEM) over fp32 operands pre-split into tf32-exact high and low parts.  This is the GPT
+ * trunk's GEMM (HF Conv1D x@W+b in GPT2Block, gpt/model.py:149-173 via transformers modeling_gpt2.py):
+ * token-exact sampling needs fp32-class logits.  With split_k > 1 the launch fills every SM for the
+ * M = n_utterances decode step; dtts_splitk_reduce finishes the tile (fixed summation order). */
+int dtts_gemm_tf32x3(const dtts_gemm_params* p, void* stream);
 
 typedef struct {
   const void* x; int x_is_f16; int ldx;   /* [M, C] */
@@ -110,6 +121,7 @@ typedef struct {
   const float* rel_k; const float* rel_v; int window;  /* WINDOW_REL: [2*window+1, head_dim] shared over heads */
   float* out_f32; int ldo32; void* out_f16; int ldo16;  /* [rows, n_heads*head_dim] head-major */
   const int* o_off;           /* [n_utt] first output row of utterance b; NULL = q_off */
+  float* out_lo; int ldo_lo;  /* decode fast path only: out_f32 receives the tf32-exact high part, out_lo the low part */
 } dtts_attention_params;
 /* softmax(scale*q.k + bias) v in exact fp32 on CUDA cores, one query per CTA.  Covers the small
  * attentions: GPT-2 causal attention incl. KV-cache decode (modeling_gpt2.py:54-72),
@@ -212,6 +224,29 @@ typedef struct {
 int dtts_sample_zp(const dtts_zp_params* p, void* stream);             /* vqvae/model_24k.py:860 */
 typedef struct { int* row_utt; int M; int n_utt; const int* utt_off; const int* utt_len; } dtts_rowutt_params;
 int dtts_fill_row_utt(const dtts_rowutt_params* p, void* stream);
+
+typedef struct {
+  const float* x; int ldx; int M, C;
+  float* hi; float* lo; int ld;
+} dtts_split_params;
+/* x = hi + lo with hi tf32-exact (low 13 mantissa bits zero): operand preparation for dtts_gemm_tf32x3. */
+int dtts_split_tf32(const dtts_split_params* p, void* stream);
+
+typedef struct {
+  const float* ws; int64_t split_stride; int n_splits; int ld_ws;  /* partials [n_splits][M][ld_ws]; n_splits may be 0 */
+  int M, N;
+  const float* bias; int act; float act_param;
+  const float* res; int ldr;           /* added after the activation */
+  float* out_f32; int ldo32;           /* v = act(sum + bias) + res, row scattered through out_row_map */
+  const int* out_row_map;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;   /* optional: y = LayerNorm(v) over the N columns (N <= 1024) */
+  float* y_f32; int ldy;               /* optional fp32 copy of y (y = v when no LayerNorm) */
+  float* y_hi; float* y_lo; int ld_hl; /* optional tf32 split of y: the next dtts_gemm_tf32x3 operand */
+} dtts_reduce_params;
+/* Deterministic split-K finish for the GPT decode step: fixed-order sum of the partial tiles + bias +
+ * activation + residual, optionally fused with the LayerNorm that follows in GPT2Block (ln_1/ln_2/ln_f,
+ * modeling_gpt2.py:262-310; gpt/model.py:322 final_norm) and the tf32 operand split of its output. */
+int dtts_splitk_reduce(const dtts_reduce_params* p, void* stream);
 
 /* library info */
 int dtts_abi_version(void);

@@ -445,3 +445,62 @@ def test_layout_and_small_ops(dlib):
     zp = torch.zeros(M, 192, device=DEV)
     dlib.call("dtts_sample_zp", m=ml, logs=ml[:, 192:], ld=384, noise=nz, ldn=192, M=M, C=192, noise_scale=0.667, out=zp, ldo=192, row_utt=ru)
     assert torch.allclose(zp, (m_ + nz * torch.exp(logs_) * 0.667) * (ru >= 0)[:, None], atol=1e-6)
+
+
+def _split(dlib, x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    dlib.call("dtts_split_tf32", x=x, ldx=x.stride(0), M=x.shape[0], C=x.shape[1], hi=hi, lo=lo, ld=hi.stride(0))
+    return hi, lo
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 768, 768), (700, 2304, 768), (37, 3072, 768), (128, 768, 3072), (5, 8196, 768)])
+def test_gemm_tf32x3_fp32_class(dlib, M, N, K):
+    """3xTF32 on tcgen05 must be fp32-class: error comparable to an fp32 FMA GEMM, far below 1xTF32/fp16."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    A = torch.randn(M, K, generator=g, device=DEV)
+    W = torch.randn(N, K, generator=g, device=DEV) / math.sqrt(K)
+    bias = torch.randn(N, generator=g, device=DEV)
+    res = torch.randn(M, N, generator=g, device=DEV)
+    Ah, Al = _split(dlib, A)
+    Wh, Wl = _split(dlib, W)
+    assert torch.equal(Ah + Al, A) and (Ah.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    out = torch.zeros(M, N, device=DEV)
+    dlib.call("dtts_gemm_tf32x3", A=Ah, A_lo=Al, W=Wh, W_lo=Wl, M=M, N=N, K=K, lda=K, ldw=K, taps=1, tap_shift0=0, tap_stride=1,
+              bias=bias, res=res, ldr=N, out_f32=out, ldo32=N, act=L.ACT_GELU_NEW, alpha=1.0, split_k=1)
+    ref = gemm_ref(A, W, N, bias=bias, res=res, act=L.ACT_GELU_NEW)
+    err = (out.double() - ref).abs().max().item()
+    # tensor-core fp32 accumulation truncates: ~2e-6 relative over K=768 (an fp16/1xTF32 GEMM is ~5e-4)
+    assert err < (1.2e-5 if K <= 1024 else 4e-5) * max(1.0, ref.abs().max().item()), err   # decode uses split-K for K=3072
+
+
+@pytest.mark.parametrize("M,N,K,S", [(128, 768, 3072, 12), (128, 2304, 768, 4), (16, 3072, 768, 3), (128, 768, 768, 12)])
+def test_gemm_tf32x3_splitk_reduce_layernorm(dlib, M, N, K, S):
+    g = torch.Generator(device=DEV).manual_seed(S + N)
+    A = torch.randn(M, K, generator=g, device=DEV)
+    W = torch.randn(N, K, generator=g, device=DEV) / math.sqrt(K)
+    bias, res = torch.randn(N, generator=g, device=DEV), torch.randn(M, N, generator=g, device=DEV)
+    gamma, beta = torch.randn(N, generator=g, device=DEV), torch.randn(N, generator=g, device=DEV)
+    Ah, Al = _split(dlib, A)
+    Wh, Wl = _split(dlib, W)
+    ws = torch.full((S, M, N), float("nan"), device=DEV)
+    dlib.call("dtts_gemm_tf32x3", A=Ah, A_lo=Al, W=Wh, W_lo=Wl, M=M, N=N, K=K, lda=K, ldw=K, taps=1, tap_shift0=0, tap_stride=1,
+              out_f32=ws, ldo32=N, act=0, alpha=1.0, split_k=S, split_stride=M * N)
+    n_splits = -(-(K // 32) // (-(-(K // 32) // S)))
+    x = torch.zeros(M, N, device=DEV)
+    ln = N <= 1024
+    y32, yh, yl = (torch.zeros(M, N, device=DEV) for _ in range(3))
+    dlib.call("dtts_splitk_reduce", ws=ws, split_stride=M * N, n_splits=n_splits, ld_ws=N, M=M, N=N, bias=bias, act=0,
+              res=res, ldr=N, out_f32=x, ldo32=N, ln_gamma=gamma if ln else None, ln_beta=beta if ln else None, ln_eps=1e-5,
+              y_f32=y32, ldy=N, y_hi=yh, y_lo=yl, ld_hl=N)
+    ref = gemm_ref(A, W, N, bias=bias, res=res)
+    assert (x.double() - ref).abs().max().item() < 1.2e-5 * max(1.0, ref.abs().max().item())
+    yref = torch.nn.functional.layer_norm(ref, (N,), gamma.double(), beta.double(), 1e-5) if ln else ref
+    assert (y32.double() - yref).abs().max().item() < 5e-5 * max(1.0, yref.abs().max().item())
+    assert torch.equal(yh + yl, y32)
+    # bit-reproducible
+    x2 = torch.zeros(M, N, device=DEV)
+    dlib.call("dtts_gemm_tf32x3", A=Ah, A_lo=Al, W=Wh, W_lo=Wl, M=M, N=N, K=K, lda=K, ldw=K, taps=1, tap_shift0=0, tap_stride=1,
+              out_f32=ws, ldo32=N, act=0, alpha=1.0, split_k=S, split_stride=M * N)
+    dlib.call("dtts_splitk_reduce", ws=ws, split_stride=M * N, n_splits=n_splits, ld_ws=N, M=M, N=N, bias=bias, act=0,
+              res=res, ldr=N, out_f32=x2, ldo32=N)
+    assert torch.equal(x, x2)

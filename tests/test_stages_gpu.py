@@ -71,6 +71,16 @@ def test_gpt_latents(model, golden):
     assert relrms(cap, lx["latent"]) < 1e-4
 
 
+def test_gpt_fp32_simt_mode_tokens(weights, golden, dlib):
+    """The exact-fp32 CUDA-core GPT mode (dtype=float32) stays token-exact too."""
+    from detail_tts_b200.gpt import UnifiedVoice
+    fx = golden["gpt"]
+    g32 = UnifiedVoice(weights, DEV, torch.float32)
+    codes = g32.inference_speech_tortoise(fx["refer"].to(DEV), fx["lengths"].tolist(), fx["text"], do_sample=False,
+                                          repetition_penalty=2.0, max_generate_length=fx["G"])
+    assert torch.equal(codes.cpu(), fx["greedy"])
+
+
 def test_gpt_fp16_mode_runs(weights, golden, dlib):
     """tcgen05 (fp16 operand) GPT: logits-level agreement is looser; check the latents stay close."""
     from detail_tts_b200.gpt import UnifiedVoice
