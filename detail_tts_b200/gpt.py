@@ -124,6 +124,141 @@ class _Trunk:
         self.ln_f = (f32(p + "ln_f.weight"), f32(p + "ln_f.bias"))
 
 
+
+class _DecodeState:
+    """All device state of a KV-cached decode over B utterances, with fixed addresses: the decode step is a
+    recorded launch Plan over these buffers (position / history length come from the device-side `step`), which
+    is what makes it capturable into ONE CUDA graph and replayable with no per-token marshalling."""
+
+    def __init__(self, gpt, B, Pmax, G, sampling):
+        do_sample, penalty, temperature, top_p, top_k, suppress_token = sampling
+        self.gpt, self.B, self.G = gpt, B, G
+        dev, dt = gpt.device, gpt.dtype
+        self.stride = stride = Pmax + 1 + G                  # KV arena rows per utterance
+        self.arena = [torch.zeros(B * stride, 3 * D_MODEL, dtype=dt, device=dev) for _ in range(N_LAYERS)]
+        self.ld_ids = ld_ids = Pmax + 1 + G + 1
+        # HF repetition penalty sees the whole row: P fake 1's, 8192, then generated ids.  Rows are right-aligned so
+        # that column n_ids0+s is generated token s for every row (extra leading 1's do not change the penalised set).
+        self.ids = torch.ones(B, ld_ids, dtype=torch.long, device=dev)
+        self.n_ids0 = n_ids0 = Pmax + 1
+        e = lambda *shape, d=torch.float32: torch.empty(*shape, dtype=d, device=dev)  # noqa: E731
+        self.xs, self.hn, self.t32 = e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL)
+        LDL = gpt.mel_head.N if gpt.tf32x3 else VOCAB          # logits row pitch (head padded to a multiple of 4)
+        self.logits = e(B, LDL)
+        self.probs = torch.zeros(B, VOCAB, dtype=torch.float32, device=dev)
+        self.argmax = torch.zeros(B, dtype=torch.long, device=dev)
+        self.nxt = torch.zeros(B, dtype=torch.long, device=dev)
+        self.unfinished = torch.ones(B, dtype=torch.int32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.kv_row = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.kv_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.kv_base = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.k_off = _i32([b * stride for b in range(B)], dev)
+        self.latents = torch.zeros(B, G + 1, D_MODEL, dtype=torch.float32, device=dev)
+        iota = torch.arange(B, dtype=torch.int32, device=dev)
+        ones = torch.ones(B, dtype=torch.int32, device=dev)
+        xs, hn, t32, arena, kv_row, kv_len, k_off = self.xs, self.hn, self.t32, self.arena, self.kv_row, self.kv_len, self.k_off
+        lib = ops._lib.lib()
+        T = gpt.trunk
+        if gpt.tf32x3:
+            xh, xl, ah, al, uh, ul = e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL), e(B, 4 * D_MODEL), e(B, 4 * D_MODEL)
+
+            def splits(pw):      # fill the SMs: (N/64 column tiles) x split_k CTAs
+                return ops.n_splits_for(pw.K, max(1, round(gpt.n_sm / ((pw.N + 63) // 64))))
+            ly0 = T.layers[0]
+            S = {k: splits(ly0[k]) for k in ("attn", "proj", "fc", "out")}
+            ws = e(max(S[k] * B * ly0[k].N for k in S))
+            wsv = {k: ws[:S[k] * B * ly0[k].N].view(S[k], B, ly0[k].N) for k in S}
+        else:
+            hdt, adt, udt = e(B, D_MODEL, d=dt), e(B, D_MODEL, d=dt), e(B, 4 * D_MODEL, d=dt)
+        _o = gpt._o
+
+        def head():
+            """t32 (ln_f'd hidden) -> final_norm -> hn (latent) -> mel_head logits -> HF processor chain"""
+            if gpt.tf32x3:
+                ops.splitk_reduce(None, 0, B, D_MODEL, res=t32, ln=gpt.final_norm, y32=hn, y_hi=xh, y_lo=xl)
+                ops.gemm_tf32x3(xh, xl, gpt.mel_head, self.logits)
+            else:
+                ops.layernorm(t32, *gpt.final_norm, out32=hn, **({"out16": hdt} if dt == torch.float16 else {}))
+                ops.gemm(hdt if dt == torch.float16 else hn, gpt.mel_head, out32=self.logits)
+            lib.call("dtts_process_logits", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
+                     n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                     do_sample=int(do_sample), suppress_token=suppress_token, probs=self.probs, ldp=VOCAB, argmax=self.argmax)
+
+        with lib.record() as self.head_plan:
+            head()
+        with lib.record() as self.append_plan:
+            lib.call("dtts_append_token", n_rows=B, next=self.nxt, ids=self.ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=self.step,
+                     unfinished=self.unfinished, stop_token=STOP_MEL, tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos,
+                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
+                     kv_pos_rows=self.kv_base)
+        with lib.record() as self.plan:
+            if gpt.tf32x3:
+                ops.splitk_reduce(None, 0, B, D_MODEL, res=xs, ln=T.layers[0]["ln1"], y_hi=xh, y_lo=xl)
+                for l, ly in enumerate(T.layers):
+                    ops.gemm_tf32x3(xh, xl, ly["attn"], wsv["attn"], split_k=S["attn"])
+                    ops.splitk_reduce(wsv["attn"], S["attn"], B, 3 * D_MODEL, bias=ly["attn"].bias, out32=arena[l],
+                                      out_row_map=kv_row)
+                    ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
+                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=ah, out_lo=al)
+                    ops.gemm_tf32x3(ah, al, ly["proj"], wsv["proj"], split_k=S["proj"])
+                    ops.splitk_reduce(wsv["proj"], S["proj"], B, D_MODEL, bias=ly["proj"].bias, res=xs, out32=xs,
+                                      ln=ly["ln2"], y_hi=xh, y_lo=xl)
+                    ops.gemm_tf32x3(xh, xl, ly["fc"], wsv["fc"], split_k=S["fc"])
+                    ops.splitk_reduce(wsv["fc"], S["fc"], B, 4 * D_MODEL, bias=ly["fc"].bias, act=ops.ACT_GELU_NEW,
+                                      y_hi=uh, y_lo=ul)
+                    ops.gemm_tf32x3(uh, ul, ly["out"], wsv["out"], split_k=S["out"])
+                    if l + 1 < len(T.layers):
+                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
+                                          ln=T.layers[l + 1]["ln1"], y_hi=xh, y_lo=xl)
+                    else:
+                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
+                                          ln=T.ln_f, y32=t32)
+            else:
+                for l, ly in enumerate(T.layers):
+                    ops.layernorm(xs, *ly["ln1"], **_o(hdt))
+                    ops.gemm(hdt, ly["attn"], out_row_map=kv_row, **_o(arena[l]))
+                    ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
+                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, **_o(adt))
+                    ops.gemm(adt, ly["proj"], res=xs, out32=xs)
+                    ops.layernorm(xs, *ly["ln2"], **_o(hdt))
+                    ops.gemm(hdt, ly["fc"], act=ops.ACT_GELU_NEW, **_o(udt))
+                    ops.gemm(udt, ly["out"], res=xs, out32=xs)
+                ops.layernorm(xs, *T.ln_f, out32=t32)
+            head()
+        self.graph = None
+        self.eager_runs = 0
+
+    def reset(self, P):
+        """Per-call reset: history ids, finished flags, step counter, per-utterance KV base positions."""
+        dev = self.ids.device
+        self.ids.fill_(1)
+        self.ids[:, self.n_ids0 - 1] = START_MEL
+        self.unfinished.fill_(1)
+        self.step.zero_()
+        self.kv_base.copy_(torch.tensor([p + 1 for p in P], dtype=torch.int32), non_blocking=False)
+
+    def run_step(self, use_graph):
+        if self.graph is not None:
+            self.graph.replay()
+            return
+        self.plan.run()              # eager at least once (one-time function attributes / tensor maps)
+        self.eager_runs += 1
+        if use_graph and self.eager_runs >= 1:
+            # capture WITHOUT torch.cuda.graph(): its __enter__ calls empty_cache(), which would make every later
+            # stage of the pipeline re-cudaMalloc its buffers on every call.
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                self.plan.run()
+                g.capture_end()
+            cur.wait_stream(side)
+            self.graph = g
+
+
 class UnifiedVoice:
     def __init__(self, W, device="cuda", dtype="tf32x3"):
         """dtype: "tf32x3" (default: fp32-class 3xTF32 GEMMs on tcgen05 tensor cores), torch.float32 (exact fp32
@@ -148,7 +283,8 @@ class UnifiedVoice:
         self.max_mel_positions = self.mel_pos.shape[0]
         self.last_latents = None
         self.last_lengths = None
-        self.use_cuda_graph = True      # replay the 74-launch decode step as one CUDA graph
+        self.use_cuda_graph = True      # replay the ~95-launch decode step as one CUDA graph
+        self._states = {}
 
     # ------------------------------------------------------------------------------------------
     def _o(self, t):
@@ -295,7 +431,7 @@ class UnifiedVoice:
             suppress_token = STOP_MEL
         if kw:
             raise TypeError(f"unsupported generate kwargs: {sorted(kw)}")
-        dev, dt = self.device, self.dtype
+        dev = self.device
         B = text_inputs.shape[0]
         tl = self._text_lengths(text_inputs, text_lengths)
         G = int(max_generate_length) if max_generate_length is not None else self.max_mel_positions - 3
@@ -305,152 +441,54 @@ class UnifiedVoice:
         start = torch.full((B, 1), START_MEL, dtype=torch.long, device=dev)
         x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, start, [1] * B)
         Pmax = max(P)
-        stride = Pmax + 1 + G                       # KV arena rows per utterance
-        arena = [torch.zeros(B * stride, 3 * D_MODEL, dtype=dt, device=dev) for _ in range(N_LAYERS)]
-        y = self._trunk_rows(x, seq_off, seq_len, arena, stride)
+        st = self._decode_state(B, Pmax, G, (do_sample, penalty, temperature, top_p, top_k, suppress_token))
+        st.reset(P)
+        y = self._trunk_rows(x, seq_off, seq_len, st.arena, st.stride)
 
-        # --- decode state (all on device; fixed buffers so the step is a replayable Plan) ----------
-        last_rows = _i32([seq_off[b] + seq_len[b] - 1 for b in range(B)], dev)
-        ld_ids = Pmax + 1 + G + 1
-        # HF repetition penalty sees the whole row: P fake 1's, 8192, then generated ids.  Rows are
-        # right-aligned per utterance so that column n_ids0+s is generated token s for every row.
-        ids = torch.ones(B, ld_ids, dtype=torch.long, device=dev)
-        ids[:, Pmax] = START_MEL
-        n_ids0 = Pmax + 1
-        xs = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)       # decode-step residual stream
-        hn = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
-        hdt = torch.empty(B, D_MODEL, dtype=dt, device=dev)
-        adt = torch.empty(B, D_MODEL, dtype=dt, device=dev)
-        udt = torch.empty(B, 4 * D_MODEL, dtype=dt, device=dev)
-        t32 = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
-        if self.tf32x3:
-            e32 = lambda c: torch.empty(B, c, dtype=torch.float32, device=dev)  # noqa: E731
-            xh, xl, ah, al, uh, ul = e32(D_MODEL), e32(D_MODEL), e32(D_MODEL), e32(D_MODEL), e32(4 * D_MODEL), e32(4 * D_MODEL)
-
-            def splits(pw):      # fill the SMs: (N/64 column tiles) x split_k CTAs
-                tiles = (pw.N + 63) // 64
-                return ops.n_splits_for(pw.K, max(1, round(self.n_sm / tiles)))
-            ly0 = self.trunk.layers[0]
-            S = {k: splits(ly0[k]) for k in ("attn", "proj", "fc", "out")}
-            ws = torch.empty(max(S[k] * B * ly0[k].N for k in S), dtype=torch.float32, device=dev)
-            wsv = {k: ws[:S[k] * B * ly0[k].N].view(S[k], B, ly0[k].N) for k in S}
-        LDL = self.mel_head.N if self.tf32x3 else VOCAB      # logits row pitch (head padded to a multiple of 4)
-        logits = torch.empty(B, LDL, dtype=torch.float32, device=dev)
-        probs = torch.zeros(B, VOCAB, dtype=torch.float32, device=dev)
-        argmax = torch.zeros(B, dtype=torch.long, device=dev)
-        unfinished = torch.ones(B, dtype=torch.int32, device=dev)
-        step = torch.zeros(1, dtype=torch.int32, device=dev)
-        kv_row = torch.zeros(B, dtype=torch.int32, device=dev)
-        kv_len = torch.zeros(B, dtype=torch.int32, device=dev)
-        k_off = _i32([b * stride for b in range(B)], dev)
-        iota = torch.arange(B, dtype=torch.int32, device=dev)
-        ones = torch.ones(B, dtype=torch.int32, device=dev)
-        # per-utterance KV position of generated token s is P_b + 1 + s; kv_row/kv_len need per-row
-        # bases, so keep them as (base + step) computed by a tiny kernel: base arrays below.
-        latents = torch.zeros(B, G + 1, D_MODEL, dtype=torch.float32, device=dev)
-
-        lib = ops._lib.lib()
-
-        def head(src_rows_x, M, first):
-            """ln_f'd hidden -> final_norm -> logits -> processed probs/argmax"""
-            if self.tf32x3:
-                ops.splitk_reduce(None, 0, B, D_MODEL, res=src_rows_x, ln=self.final_norm, y32=hn, y_hi=xh, y_lo=xl)
-                ops.gemm_tf32x3(xh, xl, self.mel_head, logits)
-            else:
-                ops.layernorm(src_rows_x, *self.final_norm, out32=hn, **({"out16": hdt} if dt == torch.float16 else {}))
-                ops.gemm(hdt if dt == torch.float16 else hn, self.mel_head, out32=logits)
-            lib.call("dtts_process_logits", logits=logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=ids, ld_ids=ld_ids,
-                     n_ids=n_ids0, step_dev=step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
-                     do_sample=int(do_sample), suppress_token=suppress_token, probs=probs, ldp=VOCAB, argmax=argmax)
-
-        # first token: from the prefill's last position of every utterance
-        y_last = y.index_select(0, last_rows.long())
-        head(y_last, B, True)
-        latents[:, 0].copy_(hn)
-
-        kv_base = _i32([P[b] + 1 for b in range(B)], dev)        # KV position of generated token 0
-
-        with lib.record() as plan:
-            if self.tf32x3:
-                L_ = self.trunk.layers
-                ops.splitk_reduce(None, 0, B, D_MODEL, res=xs, ln=L_[0]["ln1"], y_hi=xh, y_lo=xl)
-                for l, ly in enumerate(L_):
-                    ops.gemm_tf32x3(xh, xl, ly["attn"], wsv["attn"], split_k=S["attn"])
-                    ops.splitk_reduce(wsv["attn"], S["attn"], B, 3 * D_MODEL, bias=ly["attn"].bias, out32=arena[l],
-                                      out_row_map=kv_row)
-                    ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
-                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=ah, out_lo=al)
-                    ops.gemm_tf32x3(ah, al, ly["proj"], wsv["proj"], split_k=S["proj"])
-                    ops.splitk_reduce(wsv["proj"], S["proj"], B, D_MODEL, bias=ly["proj"].bias, res=xs, out32=xs,
-                                      ln=ly["ln2"], y_hi=xh, y_lo=xl)
-                    ops.gemm_tf32x3(xh, xl, ly["fc"], wsv["fc"], split_k=S["fc"])
-                    ops.splitk_reduce(wsv["fc"], S["fc"], B, 4 * D_MODEL, bias=ly["fc"].bias, act=ops.ACT_GELU_NEW,
-                                      y_hi=uh, y_lo=ul)
-                    ops.gemm_tf32x3(uh, ul, ly["out"], wsv["out"], split_k=S["out"])
-                    if l + 1 < len(L_):
-                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
-                                          ln=L_[l + 1]["ln1"], y_hi=xh, y_lo=xl)
-                    else:
-                        ops.splitk_reduce(wsv["out"], S["out"], B, D_MODEL, bias=ly["out"].bias, res=xs, out32=xs,
-                                          ln=self.trunk.ln_f, y32=t32)
-                head(t32, B, False)
-            for l, ly in enumerate([] if self.tf32x3 else self.trunk.layers):
-                ops.layernorm(xs, *ly["ln1"], **self._o(hdt))
-                ops.gemm(hdt, ly["attn"], out_row_map=kv_row, **self._o(arena[l]))
-                ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
-                              ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, **self._o(adt))
-                ops.gemm(adt, ly["proj"], res=xs, out32=xs)
-                ops.layernorm(xs, *ly["ln2"], **self._o(hdt))
-                ops.gemm(hdt, ly["fc"], act=ops.ACT_GELU_NEW, **self._o(udt))
-                ops.gemm(udt, ly["out"], res=xs, out32=xs)
-            if not self.tf32x3:
-                ops.layernorm(xs, *self.trunk.ln_f, out32=t32)
-                head(t32, B, False)
-
-        def append(nxt):
-            lib.call("dtts_append_token", n_rows=B, next=nxt, ids=ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=step,
-                     unfinished=unfinished, stop_token=STOP_MEL, tok_emb=self.mel_embedding, pos_emb=self.mel_pos,
-                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
-                     kv_pos_rows=kv_base)
+        # first token: from the prefill's last position (the <start_mel> token) of every utterance
+        last_rows = torch.tensor([seq_off[b] + seq_len[b] - 1 for b in range(B)], dtype=torch.long, device=dev)
+        torch.index_select(y, 0, last_rows, out=st.t32)
+        st.head_plan.run()
+        st.latents[:, 0].copy_(st.hn)
 
         n_gen = 0
-        graph = None
-        use_graph = self.use_cuda_graph
         for s in range(G):
             if do_sample:
-                nxt = (multinomial(probs) if multinomial is not None else torch.multinomial(probs, 1)).reshape(B)
-                nxt = nxt.to(dev)
+                nxt = (multinomial(st.probs) if multinomial is not None else torch.multinomial(st.probs, 1)).reshape(B)
+                st.nxt.copy_(nxt)
             else:
-                nxt = argmax
-            append(nxt)                      # ids[:, n_ids0+s] = token s; xs = emb(token s) + mel_pos[s+1]; step++
+                st.nxt.copy_(st.argmax)
+            st.append_plan.run()     # ids[:, n_ids0+s] = token s; xs = emb(token s) + mel_pos[s+1]; KV row/len; step++
             n_gen = s + 1
             if s + 1 >= G:
                 break
             if (s + 1) % sync_every == 0 or B == 1:
-                if int(unfinished.sum()) == 0:
+                if int(st.unfinished.sum()) == 0:
                     break
-            # (append_token also set this step's KV row/length: position P_b + 1 + s of utterance b)
-            if graph is not None:
-                graph.replay()
-            else:
-                plan.run()          # first step eagerly (one-time attribute/tensor-map setup), then capture
-                if use_graph and G > 2:
-                    graph = torch.cuda.CUDAGraph()
-                    torch.cuda.synchronize()
-                    with torch.cuda.graph(graph):
-                        plan.run()
-                    # the capture does not execute: nothing to undo
-            latents[:, s + 1].copy_(hn)
-        codes = ids[:, n_ids0:n_ids0 + n_gen].clone()
+            st.run_step(self.use_cuda_graph)
+            st.latents[:, s + 1].copy_(st.hn)
+        codes = st.ids[:, st.n_ids0:st.n_ids0 + n_gen].clone()
         # trim trailing all-pad columns produced between host checks
         if n_gen > 1:
             fin = (codes == STOP_MEL)
             done_at = torch.where(fin.any(1), fin.float().argmax(1) + 1, torch.full((B,), n_gen, device=dev))
             n_keep = int(done_at.max())
             codes = codes[:, :n_keep]
-        self.last_latents = latents
-        self.last_plan = plan
+        self.last_latents = st.latents
+        self.last_plan = st.plan
         return codes
+
+    def _decode_state(self, B, Pmax, G, sampling):
+        """Persistent decode workspace (KV arena, step buffers, recorded launch plans, captured CUDA graph) for one
+        (batch, prefix capacity, generation cap, sampling config): reused across calls, so the per-call cost is a
+        few small resets instead of re-recording / re-capturing ~95 launches."""
+        key = (B, Pmax, G, sampling)
+        st = self._states.get(key)
+        if st is None:
+            if len(self._states) >= 4:
+                self._states.clear()
+            st = self._states[key] = _DecodeState(self, B, Pmax, G, sampling)
+        return st
 
     inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528
 
