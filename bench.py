@@ -152,7 +152,7 @@ def gemm_roofline(model, lib, pk):
     plan = eng._plans[False]
     st = torch.cuda.current_stream()
     import ctypes
-    valid_rows = sum(eng.lay.lens)
+    rows_by_M = {eng.lay1.M: sum(eng.lay1.lens), eng.lay.M: sum(eng.lay.lens), eng.lay_i.M: sum(eng.lay_i.lens)}
     evs, flops = [], []
     # L2 is not flushed inside an eval on purpose: this is the in-situ duration inside the step
     for fn, s in plan.calls:
@@ -166,8 +166,7 @@ def gemm_roofline(model, lib, pk):
         assert rc == 0
         e1.record(st)
         evs.append((e0, e1))
-        rows = valid_rows if s.M >= eng.lay.M else valid_rows // 2
-        flops.append(2.0 * rows * s.N * s.K * s.taps)
+        flops.append(2.0 * rows_by_M[s.M] * s.N * s.K * s.taps)   # algorithmic: valid (non-separator) rows only
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in evs]
     tot_ms, tot_fl = sum(ms), sum(flops)

@@ -191,6 +191,19 @@ zp_kernel(const dtts_zp_params p) {
 }
 
 __global__ void __launch_bounds__(256)
+copy_utts_kernel(const dtts_copy_utts_params p) {
+  const int b = blockIdx.y;
+  const int c8 = p.C >> 3;   // 16-byte chunks per row
+  const long total = (long)p.utt_len[b] * c8;
+  const __half* s = (const __half*)p.src + (long)p.src_off[b] * p.ld_src;
+  __half* d = (__half*)p.dst + (long)p.dst_off[b] * p.ld_dst;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / c8), c = (int)(idx % c8) * 8;
+    *reinterpret_cast<uint4*>(d + (long)r * p.ld_dst + c) = *reinterpret_cast<const uint4*>(s + (long)r * p.ld_src + c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
 rowutt_kernel(const dtts_rowutt_params p) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.M) return;
@@ -294,6 +307,17 @@ extern "C" int dtts_sample_zp(const dtts_zp_params* p, void* stream) {
   return 0;
 }
 
+extern "C" int dtts_copy_utt_rows(const dtts_copy_utts_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->src && p->dst && p->src_off && p->dst_off && p->utt_len, "copy_utt_rows: null argument");
+  DTTS_REQUIRE(p->C % 8 == 0 && p->ld_src % 8 == 0 && p->ld_dst % 8 == 0, "copy_utt_rows: C/ld must be multiples of 8");
+  DTTS_REQUIRE(((((uintptr_t)p->src) | ((uintptr_t)p->dst)) & 15) == 0, "copy_utt_rows: pointers must be 16-byte aligned");
+  if (p->n_utt <= 0) return 0;
+  dim3 grid(32, p->n_utt);
+  copy_utts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("copy_utt_rows");
+  return 0;
+}
+
 extern "C" int dtts_fill_row_utt(const dtts_rowutt_params* p, void* stream) {
   DTTS_REQUIRE(p && p->row_utt && p->utt_off && p->utt_len, "fill_row_utt: null argument");
   if (p->M <= 0) return 0;
@@ -323,6 +347,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_logits_params); SZ(dtts_append_params); SZ(dtts_pstep_params); SZ(dtts_bct2rows_params);
   SZ(dtts_rows2bct_params); SZ(dtts_eltwise_params); SZ(dtts_embed_params); SZ(dtts_repeat_rows_params);
   SZ(dtts_mean_rows_params); SZ(dtts_tsemb_params); SZ(dtts_couple_params); SZ(dtts_zp_params);
-  SZ(dtts_rowutt_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
+  SZ(dtts_rowutt_params); SZ(dtts_copy_utts_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
   return -1;
 }

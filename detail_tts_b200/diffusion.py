@@ -275,16 +275,34 @@ class _Engine:
             self.lay = layF
         M2 = self.lay.M
         z = lambda c, d: torch.zeros(M2, c, dtype=d, device=dev)  # noqa: E731
+        # Integrator layout.  The unconditional branch's code embedding is `unconditioned_embedding` broadcast over
+        # frames, so its conditioning_timestep_integrator output depends only on (timestep, frame count), not on the
+        # utterance: with `both`, it is evaluated ONCE per distinct length and copied to every
+        # utterance of that length (bit-identical to evaluating it per utterance).
+        if both:
+            uniq = sorted(set(layF.lens))
+            uidx = [uniq.index(n) for n in layF.lens]
+            self.lay_i = RowsLayout(layF.lens + uniq, layF.gap, dev)
+            assert self.lay_i.offs[:layF.n] == layF.offs
+            B = layF.n
+            self.copy_src = _i32(self.lay_i.offs[:B] + [self.lay_i.offs[B + u] for u in uidx], dev)
+        else:
+            self.lay_i = self.lay
+        Mi = self.lay_i.M
+        zi = lambda c, d: torch.zeros(Mi, c, dtype=d, device=dev)  # noqa: E731
         # constant code embedding rows: precomputed (cond) / unconditioned_embedding broadcast (uncond)
-        self.ce0 = z(MODEL_CH, torch.float32)
-        unc = torch.zeros(M, MODEL_CH, dtype=torch.float32, device=dev)
-        unc[layF.row_utt >= 0] = model.uncond
+        self.ce0 = zi(MODEL_CH, torch.float32)
         if both:
             self.ce0[:M] = pre_rows
-            self.ce0[M:] = unc
+            self.ce0[M:][self.lay_i.row_utt[M:] >= 0] = model.uncond
         else:
-            self.ce0.copy_(unc if conditioning_free else pre_rows)
-        self.c32 = z(MODEL_CH, torch.float32)
+            if conditioning_free:
+                self.ce0[layF.row_utt >= 0] = model.uncond
+            else:
+                self.ce0.copy_(pre_rows)
+        self.c32 = zi(MODEL_CH, torch.float32)
+        self.ci16 = zi(MODEL_CH, F16)
+        self.buf_i = _Buf(Mi, dev) if both else None
         self.h32 = z(MODEL_CH, torch.float32)
         self.cat = z(2 * MODEL_CH, F16)
         self.buf = _Buf(M2, dev)
@@ -292,9 +310,10 @@ class _Engine:
         self.x32 = torch.zeros(M, IN_CH, dtype=torch.float32, device=dev)
         self.x16 = torch.zeros(M, IN_CH, dtype=F16, device=dev)
         self.noise = torch.zeros(M, IN_CH, dtype=torch.float32, device=dev)
-        self.film = torch.zeros(self.lay.n, len(model.resblocks), 2 * MODEL_CH, dtype=torch.float32, device=dev)
-        self.film_idx0 = torch.zeros(self.lay.n, dtype=torch.int32, device=dev)
-        self.film_idx_utt = _i32([b % layF.n for b in range(self.lay.n)], dev)
+        nf = max(self.lay.n, self.lay_i.n)
+        self.film = torch.zeros(nf, len(model.resblocks), 2 * MODEL_CH, dtype=torch.float32, device=dev)
+        self.film_idx0 = torch.zeros(nf, dtype=torch.int32, device=dev)
+        self.film_idx_utt = _i32([b % layF.n for b in range(nf)], dev)
         self._plans = {}
 
     def set_state(self, x_bct):
@@ -308,12 +327,21 @@ class _Engine:
         with L.record() as plan:
             r = 0
             src = self.ce0
+            lay_i = self.lay_i
+            buf_i = self.buf_i if self.both else buf
+            assert not (self.both and per_utt), "per-utterance timesteps are only supported for single-branch evals"
             for i, (rb, at) in enumerate(m.integrator):
-                self.m._res_block(rb, src, self.c32, lay, buf, self.film[:, r], fidx)
+                self.m._res_block(rb, src, self.c32, lay_i, buf_i, self.film[:, r], fidx)
                 last = i == len(m.integrator) - 1
-                self.m._attn_block(at, self.c32, lay, buf, out16=self.cat[:, MODEL_CH:] if last else None)
+                dst16 = None
+                if last:
+                    dst16 = self.ci16 if self.both else self.cat[:, MODEL_CH:]
+                self.m._attn_block(at, self.c32, lay_i, buf_i, out16=dst16)
                 src = self.c32
                 r += 1
+            if self.both:
+                L.call("dtts_copy_utt_rows", src=self.ci16, ld_src=MODEL_CH, C=MODEL_CH, n_utt=lay.n, src_off=self.copy_src,
+                       dst_off=lay.off, utt_len=lay.len, dst=self.cat[:, MODEL_CH:], ld_dst=2 * MODEL_CH)
             ops.gemm(self.x16, m.inp_block, out16=self.cat[:M, :MODEL_CH], row_utt=self.lay1.row_utt)
             if self.both:
                 ops.gemm(self.x16, m.inp_block, out16=self.cat[M:, :MODEL_CH], row_utt=self.lay1.row_utt)

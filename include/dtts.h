@@ -222,6 +222,15 @@ typedef struct {
   float* out; int ldo; const int* row_utt;
 } dtts_zp_params;
 int dtts_sample_zp(const dtts_zp_params* p, void* stream);             /* vqvae/model_24k.py:860 */
+typedef struct {
+  const void* src; int ld_src; int C; int n_utt;      /* fp16 rows */
+  const int* src_off; const int* dst_off; const int* utt_len;   /* [n_utt] */
+  void* dst; int ld_dst;
+} dtts_copy_utts_params;
+/* dst rows of utterance b <- src rows starting at src_off[b] (fp16): broadcasts the classifier-free-guidance
+ * branch's timestep-integrator output, which depends only on (timestep, frame count), to every utterance of
+ * that length (vqvae/diff_model.py:283-299, unconditioned_embedding.repeat + conditioning_timestep_integrator). */
+int dtts_copy_utt_rows(const dtts_copy_utts_params* p, void* stream);
 typedef struct { int* row_utt; int M; int n_utt; const int* utt_off; const int* utt_len; } dtts_rowutt_params;
 int dtts_fill_row_utt(const dtts_rowutt_params* p, void* stream);
 
