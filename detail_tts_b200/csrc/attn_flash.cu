@@ -19,6 +19,8 @@ constexpr int NWARP = BQ / 16;
 constexpr int NTHR = NWARP * 32;
 constexpr int NT = BKV / 8;        // score n-tiles per key tile
 constexpr int MAX_BIAS = 513;
+constexpr int BIAS_PAD = 80;       // table padded with its end values: one clamp per (thread, key tile) instead of per score
+static_assert(BIAS_PAD >= BKV + 16 + 9, "padding must cover one key tile + one warp's query rows");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -59,7 +61,8 @@ flash48_kernel(const dtts_attention_params p) {
   __shared__ __align__(16) __half sQ[BQ][LDS];
   __shared__ __align__(16) __half sK[2][BKV][LDS];
   __shared__ __align__(16) __half sV[2][BKV][LDS];
-  __shared__ float sBias[MAX_BIAS];
+  __shared__ float sBiasPad[MAX_BIAS + 2 * BIAS_PAD];
+  float* const sBias = sBiasPad + BIAS_PAD;   // sBias[-BIAS_PAD .. 2*half + BIAS_PAD]
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int qlen = p.q_len[b], klen = p.k_len[b];
   const int q0 = qt * BQ;
@@ -78,7 +81,8 @@ flash48_kernel(const dtts_attention_params p) {
   }
   const int half = p.bias_half;
   const int nb = p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? 2 * half + 1 : 0;
-  for (int i = tid; i < nb; i += NTHR) sBias[i] = p.bias_table[h * nb + i] * LOG2E;
+  if (nb)
+    for (int i = tid - BIAS_PAD; i < nb + BIAS_PAD; i += NTHR) sBias[i] = p.bias_table[h * nb + min(max(i, 0), nb - 1)] * LOG2E;
 
   auto load_kv = [&](int t, int buf) {
     const int k0 = t * BKV;
@@ -150,15 +154,20 @@ flash48_kernel(const dtts_attention_params p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[nt][e] = fmaf(s[nt][e], sc2, ub);
     } else {
-      const int base = k0 + tig * 2 - qi0 + half;   // index for (nt=0, e=0); + nt*8 + (e&1) - (e>>1)*8
+      // table index of (nt, e): base + nt*8 + (e&1) - (e>>1)*8, i.e. rows g+8 at n-tile nt reuse the pair of rows g at
+      // n-tile nt-1: NT+1 pair loads per thread.  The padded table makes one clamp of `base` per tile exact.
+      int base = k0 + tig * 2 - qi0 + half;
+      base = min(max(base, -BIAS_PAD + 8), 2 * half + BIAS_PAD - 8 * NT);
+      const float* bp = sBias + base;
+      float b0 = bp[-8], b1 = bp[-7];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int r = base + nt * 8 + (e & 1) - (e >> 1) * 8;
-          r = min(max(r, 0), 2 * half);
-          s[nt][e] = fmaf(s[nt][e], sc2, sBias[r]);
-        }
+        const float c0 = bp[nt * 8], c1 = bp[nt * 8 + 1];
+        s[nt][0] = fmaf(s[nt][0], sc2, c0);
+        s[nt][1] = fmaf(s[nt][1], sc2, c1);
+        s[nt][2] = fmaf(s[nt][2], sc2, b0);
+        s[nt][3] = fmaf(s[nt][3], sc2, b1);
+        b0 = c0; b1 = c1;
       }
     }
     if (k0 + BKV > klen) {

@@ -1,4 +1,5 @@
-// attn_simt.cu -- exact-fp32 attention on CUDA cores, one (query, head, utterance) per CTA.
+// attn_simt.cu -- exact-fp32 attention on CUDA cores: a 32-query tiled kernel, a KV-cache decode kernel and a
+// generic one-query-per-CTA fallback.
 // Covers every small attention on the path with one kernel:
 //   GPT-2 causal attention, prefill and KV-cache decode  (transformers modeling_gpt2.py:54-72)
 //   MelStyleEncoder 2-head attention, temperature sqrt(d_model)  (vqvae/modules/modules.py:565-639)
@@ -89,6 +90,191 @@ attention_simt_kernel(const dtts_attention_params p) {
     if (p.out_f32) p.out_f32[orow * p.ldo32 + h * hd + threadIdx.x] = t;
     if (p.out_f16) ((__half*)p.out_f16)[orow * p.ldo16 + h * hd + threadIdx.x] = __float2half_rn(t);
   }
+}
+
+// ---- Tiled variant for everything with more than one query per utterance (GPT prefill, MelStyleEncoder,
+// enc_p, contextual_embedder / latent_conditioner): one CTA = (utterance, head, 32 queries), 8 warps x 4 queries.
+// Keys / values stream through shared memory in 64-key chunks (read from global ONCE per 32 queries instead of
+// once per query), scores are register-blocked 4 queries x 2 keys per lane, the softmax is online (running max /
+// sum per query, fp32, exact expf), P.V has lanes over the head dimension.  Same semantics as the per-query
+// kernel below: causal offset, relative-position bias table, windowed relative key/value embeddings.
+constexpr int AT_TQ = 32, AT_KT = 64, AT_WARPS = 8, AT_QPW = 4;
+
+template <typename T, int DPL>   // DPL = head-dim elements per lane: head_dim <= 32*DPL
+__global__ void __launch_bounds__(AT_WARPS * 32)
+attention_tile_kernel(const dtts_attention_params p) {
+  extern __shared__ float4 sm4[];
+  float* sm = reinterpret_cast<float*>(sm4);
+  const int hd = p.head_dim, ldks = hd + 1;
+  float* Qs = sm;                                   // [TQ][hd]   (pre-scaled)
+  float* Ks = Qs + AT_TQ * hd;                      // [KT][hd+1]
+  float* Vs = Ks + AT_KT * ldks;                    // [KT][hd]
+  float* Ps = Vs + AT_KT * hd;                      // [TQ][KT]
+  float* Rq = Ps + AT_TQ * AT_KT;                   // [TQ][2*window+1]
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_TQ;
+  const int qlen = p.q_len[b];
+  if (q0 >= qlen) return;
+  const int klen = p.k_len[b];
+  const int coff = p.causal_offset ? p.causal_offset[b] : 0;
+  int nk = klen;
+  if (p.causal) nk = min(nk, q0 + AT_TQ + coff);    // the tile's last query sees keys <= q0 + TQ - 1 + coff
+  if (nk <= 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const T* qg = (const T*)p.q + (long)p.q_off[b] * p.ldq + (long)h * p.head_stride_q;
+  const T* kg = (const T*)p.k + (long)p.k_off[b] * p.ldk + (long)h * p.head_stride_k;
+  const T* vg = (const T*)p.v + (long)p.k_off[b] * p.ldv + (long)h * p.head_stride_v;
+  for (int idx = tid; idx < AT_TQ * hd; idx += AT_WARPS * 32) {
+    const int r = idx / hd, d = idx - r * hd;
+    Qs[idx] = q0 + r < qlen ? ldf<T>(qg + (long)(q0 + r) * p.ldq + d) * p.scale : 0.f;
+  }
+  const int nw = 2 * p.window + 1;
+  const bool win = p.bias_mode == DTTS_ATTN_BIAS_WINDOW_REL, tab = p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE;
+  if (win) {
+    __syncthreads();
+    for (int idx = tid; idx < AT_TQ * nw; idx += AT_WARPS * 32) {
+      const int r = idx / nw, w = idx - r * nw;
+      float t = 0.f;
+      for (int d = 0; d < hd; ++d) t = fmaf(Qs[r * hd + d], p.rel_k[w * hd + d], t);
+      Rq[idx] = t;
+    }
+  }
+  float m_run[AT_QPW], l_run[AT_QPW], o[AT_QPW][DPL];
+#pragma unroll
+  for (int qi = 0; qi < AT_QPW; ++qi) {
+    m_run[qi] = -INFINITY; l_run[qi] = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) o[qi][dd] = 0.f;
+  }
+  const int qrow = warp * AT_QPW;            // first query (tile-local) of this warp
+  for (int k0 = 0; k0 < nk; k0 += AT_KT) {
+    __syncthreads();                         // previous chunk fully consumed (and Qs / Rq visible)
+    for (int idx = tid; idx < AT_KT * hd; idx += AT_WARPS * 32) {
+      const int j = idx / hd, d = idx - j * hd;
+      const bool ok = k0 + j < nk;
+      Ks[j * ldks + d] = ok ? ldf<T>(kg + (long)(k0 + j) * p.ldk + d) : 0.f;
+      Vs[idx] = ok ? ldf<T>(vg + (long)(k0 + j) * p.ldv + d) : 0.f;
+    }
+    __syncthreads();
+    float s[AT_QPW][2];
+#pragma unroll
+    for (int qi = 0; qi < AT_QPW; ++qi) s[qi][0] = s[qi][1] = 0.f;
+    const float* ka = Ks + lane * ldks;
+    const float* kb = Ks + (lane + 32) * ldks;
+    for (int d = 0; d < hd; d += 4) {
+      float4 qv[AT_QPW];
+#pragma unroll
+      for (int qi = 0; qi < AT_QPW; ++qi) qv[qi] = *reinterpret_cast<const float4*>(Qs + (qrow + qi) * hd + d);
+      const float a0 = ka[d], a1 = ka[d + 1], a2 = ka[d + 2], a3 = ka[d + 3];
+      const float b0 = kb[d], b1 = kb[d + 1], b2 = kb[d + 2], b3 = kb[d + 3];
+#pragma unroll
+      for (int qi = 0; qi < AT_QPW; ++qi) {
+        s[qi][0] = fmaf(qv[qi].x, a0, s[qi][0]); s[qi][0] = fmaf(qv[qi].y, a1, s[qi][0]);
+        s[qi][0] = fmaf(qv[qi].z, a2, s[qi][0]); s[qi][0] = fmaf(qv[qi].w, a3, s[qi][0]);
+        s[qi][1] = fmaf(qv[qi].x, b0, s[qi][1]); s[qi][1] = fmaf(qv[qi].y, b1, s[qi][1]);
+        s[qi][1] = fmaf(qv[qi].z, b2, s[qi][1]); s[qi][1] = fmaf(qv[qi].w, b3, s[qi][1]);
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < AT_QPW; ++qi) {
+      const int i = q0 + qrow + qi;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = k0 + lane + 32 * jj;
+        float v = s[qi][jj];
+        if (tab) {
+          int r = j - i;
+          r = r < -p.bias_half ? -p.bias_half : (r > p.bias_half ? p.bias_half : r);
+          v += p.bias_table[h * (2 * p.bias_half + 1) + r + p.bias_half];
+        } else if (win) {
+          const int r = j - i;
+          if (r >= -p.window && r <= p.window) v += Rq[(qrow + qi) * nw + r + p.window];
+        }
+        const bool ok = j < klen && (!p.causal || j <= i + coff);
+        s[qi][jj] = ok ? v : -INFINITY;
+      }
+      const float mx = warp_max(fmaxf(s[qi][0], s[qi][1]));
+      const float mn = fmaxf(m_run[qi], mx);
+      float corr = 1.f, p0 = 0.f, p1 = 0.f;
+      if (mn != -INFINITY) {
+        corr = expf(m_run[qi] - mn);
+        p0 = expf(s[qi][0] - mn);
+        p1 = expf(s[qi][1] - mn);
+      }
+      m_run[qi] = mn;
+      l_run[qi] = l_run[qi] * corr + warp_sum(p0 + p1);
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) o[qi][dd] *= corr;
+      Ps[(qrow + qi) * AT_KT + lane] = p0;
+      Ps[(qrow + qi) * AT_KT + lane + 32] = p1;
+    }
+    __syncwarp();
+    for (int j = 0; j < AT_KT; j += 4) {
+      float4 pv[AT_QPW];
+#pragma unroll
+      for (int qi = 0; qi < AT_QPW; ++qi) pv[qi] = *reinterpret_cast<const float4*>(Ps + (qrow + qi) * AT_KT + j);
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) {
+        const int d = lane + 32 * dd;
+        if (d < hd) {
+          const float v0 = Vs[j * hd + d], v1 = Vs[(j + 1) * hd + d], v2 = Vs[(j + 2) * hd + d], v3 = Vs[(j + 3) * hd + d];
+#pragma unroll
+          for (int qi = 0; qi < AT_QPW; ++qi) {
+            o[qi][dd] = fmaf(pv[qi].x, v0, o[qi][dd]); o[qi][dd] = fmaf(pv[qi].y, v1, o[qi][dd]);
+            o[qi][dd] = fmaf(pv[qi].z, v2, o[qi][dd]); o[qi][dd] = fmaf(pv[qi].w, v3, o[qi][dd]);
+          }
+        }
+      }
+    }
+    if (win) {
+#pragma unroll
+      for (int qi = 0; qi < AT_QPW; ++qi) {
+        const int i = q0 + qrow + qi;
+        for (int w = 0; w < nw; ++w) {
+          const int j = i + w - p.window;
+          if (j >= k0 && j < k0 + AT_KT) {
+            const float pj = Ps[(qrow + qi) * AT_KT + j - k0];
+#pragma unroll
+            for (int dd = 0; dd < DPL; ++dd) {
+              const int d = lane + 32 * dd;
+              if (d < hd) o[qi][dd] = fmaf(pj, p.rel_v[w * hd + d], o[qi][dd]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < AT_QPW; ++qi) {
+    const int i = q0 + qrow + qi;
+    if (i >= qlen) continue;
+    const float inv = l_run[qi] > 0.f ? 1.0f / l_run[qi] : 0.f;
+    const long orow = (long)(p.o_off ? p.o_off[b] : p.q_off[b]) + i;
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) {
+      const int d = lane + 32 * dd;
+      if (d < hd) {
+        const float t = o[qi][dd] * inv;
+        if (p.out_f32) p.out_f32[orow * p.ldo32 + h * hd + d] = t;
+        if (p.out_f16) ((__half*)p.out_f16)[orow * p.ldo16 + h * hd + d] = __float2half_rn(t);
+      }
+    }
+  }
+}
+
+template <typename T, int DPL>
+int launch_tile(const dtts_attention_params* p, cudaStream_t st) {
+  const int hd = p->head_dim;
+  const size_t smem = (size_t)(AT_TQ * hd + AT_KT * (hd + 1) + AT_KT * hd + AT_TQ * AT_KT + AT_TQ * (2 * p->window + 1) + 4) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tile_kernel<T, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(attention_tile): %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  dim3 grid(ceil_div(p->max_q_len, AT_TQ), p->n_heads, p->n_utt);
+  attention_tile_kernel<T, DPL><<<grid, AT_WARPS * 32, smem, st>>>(*p);
+  DTTS_CHECK_LAUNCH("attention_tile");
+  return 0;
 }
 
 // ---- KV-cache decode attention: ONE query per (utterance, head) against its cached keys/values.
@@ -208,6 +394,12 @@ extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) 
     return 0;
   }
   DTTS_REQUIRE(!p->out_lo, "attention_f32: out_lo (tf32 split) is only produced by the fp32 KV-cache decode path");
+  if (p->max_q_len > 1 && p->head_dim % 4 == 0 && p->head_dim <= 192 && p->window >= 0 && p->window <= 16) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hd = p->head_dim;
+    if (p->is_f16) return hd <= 64 ? launch_tile<__half, 2>(p, st) : hd <= 96 ? launch_tile<__half, 3>(p, st) : launch_tile<__half, 6>(p, st);
+    return hd <= 64 ? launch_tile<float, 2>(p, st) : hd <= 96 ? launch_tile<float, 3>(p, st) : launch_tile<float, 6>(p, st);
+  }
   const int threads = 256;
   const size_t smem = (size_t)(p->head_dim + p->max_k_len + threads) * sizeof(float);
   DTTS_REQUIRE(smem <= (size_t)max_smem, "attention_f32: too many keys for one CTA (%d)", p->max_k_len);

@@ -107,103 +107,179 @@ groupnorm_kernel(const T* __restrict__ x, int ldx, int C, int cpg, const int* __
   }
 }
 
-// Register-resident variant for the diffusion hot loop (24 channels/group, utterances up to
-// GNR_MAXR * rows-per-sweep frames): one CTA = (utterance, 2 groups); the whole [T, 48] strip is loaded
-// into registers with every load in flight at once (HBM-latency bound otherwise), statistics are exact
-// two-pass (mean, then centred sum of squares) from registers, and the normalised operand is written
-// straight from registers: x is read from HBM exactly once and nothing is staged in shared memory.
-constexpr int GNR_GPC = 2;     // groups per CTA
-constexpr int GNR_MAXR = 11;   // rows per thread (384 threads / 12 float4 columns = 32 rows per sweep -> T <= 352)
+// Register-resident variant for the diffusion hot loop (utterances up to GNR_MAXR * rows-per-sweep frames):
+// one CTA = (utterance, GPC groups); every thread owns 4-channel vectors (16 B fp32 / 8 B fp16) of MAXR
+// rows, all loads in flight at once (HBM-latency bound otherwise); the strip stays in registers in its raw
+// storage type, statistics are exact two-pass (mean, then centred sum of squares), and the normalised operand
+// is written straight from registers: x is read from HBM exactly once, nothing is staged in shared memory.
+// fp32 input: 2 groups (48 ch = 192 B per row) per CTA; fp16 input: 4 groups (96 ch = 192 B per row).
 constexpr int GNR_THREADS = 384;
+constexpr int GNR_MAXG = 4;
 
-__device__ __forceinline__ float2 block_sum2(float2 v, float2* sh) {
+// SiLU with the fast exp/rcp path (2 MUFU + 3 FMA-class ops; |rel err| ~ 2^-21, far below the fp16 operand rounding
+// that follows).  The exact expf + IEEE division of sigmoidf_ made this HBM-bound kernel instruction-bound.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int G>
+__device__ __forceinline__ void block_sum_g(float (&v)[G], float (*sh)[GNR_MAXG]) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  for (int i = 0; i < G; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < G; ++i) sh[w][i] = v[i];
   }
   __syncthreads();
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < GNR_THREADS / 32; ++i) { t.x += sh[i].x; t.y += sh[i].y; }
-  return t;
+  for (int i = 0; i < G; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < GNR_THREADS / 32; ++k) t += sh[k][i];
+    v[i] = t;
+  }
 }
 
-template <typename T>
+template <typename T> struct GnVec;
+template <> struct GnVec<float> {
+  static constexpr int N = 4;
+  typedef uint4 Raw;
+  static constexpr int MAXR = 11;   // 384 threads / 12 vector columns = 32 rows per sweep -> T <= 352
+  __device__ static __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+};
+template <> struct GnVec<__half> {
+  static constexpr int N = 4;
+  typedef uint2 Raw;
+  static constexpr int MAXR = 18;   // 384 threads / 24 vector columns = 16 rows per sweep -> T <= 288
+  __device__ static __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
+  __device__ static __forceinline__ void unpack(const uint2& u, float (&f)[4]) {
+    // opaque moves: keep the strip packed in registers (the compiler would otherwise hoist the fp32 copies of all
+    // rows across the three passes and spill)
+    uint32_t ux, uy;
+    asm volatile("mov.b32 %0, %1;" : "=r"(ux) : "r"(u.x));
+    asm volatile("mov.b32 %0, %1;" : "=r"(uy) : "r"(u.y));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ux));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&uy));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+};
+
+template <typename T, int GPC>
 __global__ void __launch_bounds__(GNR_THREADS, 2)
 groupnorm_reg_kernel(const T* __restrict__ x, int ldx, int cpg, const int* __restrict__ utt_off,
                      const int* __restrict__ utt_len, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ film_scale, const float* __restrict__ film_shift, int ld_film,
                      const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
                      __half* __restrict__ out16, int ldo16) {
-  __shared__ float2 red[GNR_THREADS / 32];
+  constexpr int VE = GnVec<T>::N;
+  __shared__ float red[GNR_THREADS / 32][GNR_MAXG];
   const int b = blockIdx.y;
-  const int cw = GNR_GPC * cpg;
+  const int cw = GPC * cpg;
   const int c0 = blockIdx.x * cw;
-  const int Q = cw >> 2;
+  const int Q = cw / VE;
   const int rs = GNR_THREADS / Q;
-  const int col4 = threadIdx.x % Q, rsub = threadIdx.x / Q;
+  const int col = threadIdx.x % Q, rsub = threadIdx.x / Q;
   const bool active = rsub < rs;
-  const int g = (col4 * 4) / cpg;   // 0 or 1
+  const int g = (col * VE) / cpg;
   const int T_ = utt_len[b];
   const long row0 = utt_off[b];
-  const T* xb = x + row0 * ldx + c0 + col4 * 4;
-  float4 v[GNR_MAXR];
+  const T* xb = x + row0 * ldx + c0 + col * VE;
+  constexpr int GNR_MAXR = GnVec<T>::MAXR;
+  typedef typename GnVec<T>::Raw Raw;
+  Raw v[GNR_MAXR];
 #pragma unroll
   for (int i = 0; i < GNR_MAXR; ++i) {
     const int r = rsub + i * rs;
-    v[i] = (active && r < T_) ? load4<T>(xb + (long)r * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (active && r < T_) ? __ldg(reinterpret_cast<const Raw*>(xb + (long)r * ldx)) : GnVec<T>::zero();
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < GNR_MAXR; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < GNR_MAXR; ++i) {
+    float f[VE];
+    GnVec<T>::unpack(v[i], f);
+#pragma unroll
+    for (int q = 0; q < VE; q += 2) s += f[q] + f[q + 1];
+  }
   const float inv_n = 1.0f / ((float)T_ * cpg);
-  float2 sm = block_sum2(make_float2(g == 0 ? s : 0.f, g == 1 ? s : 0.f), red);
-  const float mean = (g == 0 ? sm.x : sm.y) * inv_n;
+  float sg[GPC];
+#pragma unroll
+  for (int i = 0; i < GPC; ++i) sg[i] = g == i ? s : 0.f;
+  block_sum_g<GPC>(sg, red);
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPC; ++i) mean = g == i ? sg[i] * inv_n : mean;
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < GNR_MAXR; ++i) {
     const int r = rsub + i * rs;
     if (active && r < T_) {
-      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      float f[VE];
+      GnVec<T>::unpack(v[i], f);
+#pragma unroll
+      for (int q = 0; q < VE; q += 2) {
+        const float a0 = f[q] - mean, a1 = f[q + 1] - mean;
+        ss += a0 * a0 + a1 * a1;
+      }
     }
   }
-  float2 sq = block_sum2(make_float2(g == 0 ? ss : 0.f, g == 1 ? ss : 0.f), red);
-  const float rstd = rsqrtf((g == 0 ? sq.x : sq.y) * inv_n + eps);
+#pragma unroll
+  for (int i = 0; i < GPC; ++i) sg[i] = g == i ? ss : 0.f;
+  block_sum_g<GPC>(sg, red);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPC; ++i) var = g == i ? sg[i] * inv_n : var;
+  const float rstd = rsqrtf(var + eps);
   if (!active) return;
-  const int c = c0 + col4 * 4;
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-  float A_[4] = {rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w};
-  float B_[4] = {be.x - mean * A_[0], be.y - mean * A_[1], be.z - mean * A_[2], be.w - mean * A_[3]};
+  const int c = c0 + col * VE;
+  float A_[VE], B_[VE];
+#pragma unroll
+  for (int q = 0; q < VE; q += 4) {
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c + q), be = *reinterpret_cast<const float4*>(beta + c + q);
+    A_[q] = rstd * ga.x; A_[q + 1] = rstd * ga.y; A_[q + 2] = rstd * ga.z; A_[q + 3] = rstd * ga.w;
+    B_[q] = be.x - mean * A_[q]; B_[q + 1] = be.y - mean * A_[q + 1]; B_[q + 2] = be.z - mean * A_[q + 2]; B_[q + 3] = be.w - mean * A_[q + 3];
+  }
   if (film_scale) {   // (x*A+B)*(1+fs)+fb = x*A(1+fs) + B(1+fs)+fb
     const long fr = film_idx ? film_idx[b] : b;
-    const float4 fs = *reinterpret_cast<const float4*>(film_scale + fr * ld_film + c);
-    const float4 fb = *reinterpret_cast<const float4*>(film_shift + fr * ld_film + c);
-    const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { A_[q] *= f1[q]; B_[q] = B_[q] * f1[q] + f0[q]; }
+    for (int q = 0; q < VE; q += 4) {
+      const float4 fs = *reinterpret_cast<const float4*>(film_scale + fr * ld_film + c + q);
+      const float4 fb = *reinterpret_cast<const float4*>(film_shift + fr * ld_film + c + q);
+      const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { A_[q + k] *= f1[k]; B_[q + k] = B_[q + k] * f1[k] + f0[k]; }
+    }
   }
 #pragma unroll
   for (int i = 0; i < GNR_MAXR; ++i) {
     const int r = rsub + i * rs;
     if (r >= T_) break;
-    float y[4] = {v[i].x * A_[0] + B_[0], v[i].y * A_[1] + B_[1], v[i].z * A_[2] + B_[2], v[i].w * A_[3] + B_[3]};
+    float y[VE];
+    GnVec<T>::unpack(v[i], y);
+#pragma unroll
+    for (int q = 0; q < VE; ++q) y[q] = fmaf(y[q], A_[q], B_[q]);
     if (act == DTTS_ACT_SILU) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) y[q] = y[q] * sigmoidf_(y[q]);
+      for (int q = 0; q < VE; ++q) y[q] = silu_fast(y[q]);
     }
     const long orow = row0 + r;
-    if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out32) {
+#pragma unroll
+      for (int q = 0; q < VE; q += 4)
+        *reinterpret_cast<float4*>(out32 + orow * ldo32 + c + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+    }
     if (out16) {
-      __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(out16 + orow * ldo16 + c) = pk;
+      uint32_t pk[VE / 2];
+#pragma unroll
+      for (int q = 0; q < VE; q += 2) {
+        __half2 h = __floats2half2_rn(y[q], y[q + 1]);
+        pk[q / 2] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint2*>(out16 + orow * ldo16 + c) = make_uint2(pk[0], pk[1]);
     }
   }
 }
@@ -271,19 +347,21 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
   cudaStream_t st0 = (cudaStream_t)stream;
   {
     // register-resident fast path (see groupnorm_reg_kernel)
-    const int Qr = GNR_GPC * cpg / 4;
+    const int ve = 4, gpc = p->x_is_f16 ? 4 : 2, maxr = p->x_is_f16 ? GnVec<__half>::MAXR : GnVec<float>::MAXR;
+    const int Qr = gpc * cpg / ve;
     const int rs = Qr > 0 ? GNR_THREADS / Qr : 0;
-    const bool aligned = ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->x)) & 15) == 0 &&
+    const bool aligned = ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->x)) & 15) == 0 && p->ldx % ve == 0 &&
                          (!p->film_scale || (((((uintptr_t)p->film_scale) | ((uintptr_t)p->film_shift)) & 15) == 0 && p->ld_film % 4 == 0)) &&
-                         (!p->out_f32 || (((uintptr_t)p->out_f32) & 15) == 0) && (!p->out_f16 || (((uintptr_t)p->out_f16) & 7) == 0);
-    if (p->groups % GNR_GPC == 0 && rs > 0 && p->max_len > 0 && p->max_len <= GNR_MAXR * rs && aligned && cpg % 4 == 0 && cpg <= 32) {
-      dim3 grid(p->groups / GNR_GPC, p->n_utt);
+                         (!p->out_f32 || (((uintptr_t)p->out_f32) & 15) == 0) &&
+                         (!p->out_f16 || ((((uintptr_t)p->out_f16) & 7) == 0 && p->ldo16 % 4 == 0));
+    if (p->groups % gpc == 0 && rs > 0 && p->max_len > 0 && p->max_len <= maxr * rs && aligned && cpg % ve == 0 && cpg <= 32) {
+      dim3 grid(p->groups / gpc, p->n_utt);
       if (p->x_is_f16)
-        groupnorm_reg_kernel<__half><<<grid, GNR_THREADS, 0, st0>>>(
+        groupnorm_reg_kernel<__half, 4><<<grid, GNR_THREADS, 0, st0>>>(
             (const __half*)p->x, p->ldx, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
             p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
       else
-        groupnorm_reg_kernel<float><<<grid, GNR_THREADS, 0, st0>>>(
+        groupnorm_reg_kernel<float, 2><<<grid, GNR_THREADS, 0, st0>>>(
             (const float*)p->x, p->ldx, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
             p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16);
       DTTS_CHECK_LAUNCH("groupnorm_reg");
