@@ -1,0 +1,498 @@
+// attn_tc.cu -- tcgen05 flash attention for the diffusion AttentionBlock hot loop (head_dim 48, fp16 operands)
+// (vqvae/utils/diff_util.py:145-169: QKVAttentionLegacy; xtransformers.py:177-186: T5-style relative-position
+// bias added to the scores before the fp32 softmax).
+//
+// Persistent, warp-specialised, one CTA per SM.  A work item is (utterance, head, 384-query block) = three
+// 128-row query tiles that share the utterance's keys / values; a slot is one 48-key chunk of an item:
+//   warp 0      TMA producer: Q tiles (double-buffered per item) and 48-key K / V chunks through an 8-stage mbarrier
+//               ring (64-column boxes, 128B swizzle: the 48-wide head plus 16 ignored columns)
+//   warps 1-3   one tcgen05.mma issuer thread per query tile: S_t = Q_t K^T (M=128, N=48, 3 k-steps, fp32 in TMEM,
+//               two S buffers per tile) and O_t += P_t V (A = P from TMEM, B = V from shared memory MN-major, N=48)
+//   warps 4-15  three softmax warpgroups, one per query tile, ONE THREAD PER ROW: tcgen05.ld the 48 scores,
+//               scale + bias in the log2 domain, running max with lazy rescaling of O (only when the max grew by
+//               more than 2^8), exp2, row sum, fp16 P written back over S with tcgen05.st.  No shuffles, no
+//               shared-memory traffic except the bias table.
+// S_t of slot g+2 is issued right after P.V_t of slot g (it reuses that buffer), so the score MMA is never on a
+// warpgroup's critical path; the epilogue of an item (O / l -> HBM) is deferred into the next item's first slot,
+// when its last P.V has long retired.  The [F, F] score matrix never leaves TMEM.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+using namespace dtts_tc;
+
+namespace {
+
+constexpr int HD = 48;
+constexpr int BM = 128;            // query rows per tile (UMMA M)
+constexpr int NT = 3;              // query tiles per work item
+constexpr int BKV = 48;            // keys per chunk (UMMA N of S; K extent of P.V)
+constexpr int NS = 8;              // K/V ring stages
+constexpr int MAX_UTT = 512;       // utterance offsets / lengths staged in shared memory
+constexpr int Q_TILE_BYTES = BM * 128;
+constexpr int KV_TILE_BYTES = BKV * 128;
+constexpr int STAGE_BYTES = 2 * KV_TILE_BYTES;
+constexpr int BIAS_PAD = BKV;
+constexpr int SM_Q = 0;                                   // 2 buffers x NT tiles
+constexpr int SM_KV = 2 * NT * Q_TILE_BYTES;
+constexpr int SM_BAR = SM_KV + NS * STAGE_BYTES;
+constexpr int SM_META = SM_BAR + 512;
+constexpr int SM_BIAS = SM_META + 4 * MAX_UTT * 4;
+constexpr int SMEM_MAX = 227 * 1024;
+constexpr int BIAS_MAX_FLOATS = (SMEM_MAX - 1024 - SM_BIAS) / 4;   // all heads' padded tables must fit
+constexpr int NTHREADS = 128 + NT * 128;    // warpgroup 0: TMA warp + 3 MMA-issuer warps; warpgroups 1..3: softmax
+constexpr int TM_S = 0;                    // S_t buffer u at columns (2t+u)*48 (P aliases its first 24 columns)
+constexpr int TM_O = 2 * NT * BKV;         // O_t at columns 288 + t*48
+constexpr int TMEM_COLS = 512;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P <= 2^8 stays exact in fp16, fp32 sums have headroom
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// MN-major, SWIZZLE_128B shared-memory descriptor: rows of 128 B = 64 contiguous MN elements, one row per K index,
+// 8-row swizzle atoms 1024 B apart (stride byte offset); the leading byte offset (next 64 MN elements) is unused.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+struct Item { int b, h, q0, qlen, klen, nc; };
+
+// Work items are (utterance, head, query block); a CTA takes every gridDim.x-th one; a SLOT is one 48-key chunk of
+// one item.  Every role walks the same slot stream (utterance offsets / lengths are staged in shared memory).
+struct SlotIter {
+  const int* meta; int n_utt, n_heads, qblocks, stride;
+  int idx, c; Item it; bool valid;
+  __device__ __forceinline__ bool load(int i) {
+    const int total = n_utt * n_heads * qblocks;
+    for (; i < total; i += stride) {
+      it.b = i / (n_heads * qblocks);
+      const int r = i - it.b * n_heads * qblocks;
+      it.h = r / qblocks;
+      it.q0 = (r - it.h * qblocks) * (NT * BM);
+      it.qlen = meta[MAX_UTT + it.b];
+      it.klen = meta[3 * MAX_UTT + it.b];
+      it.nc = (it.klen + BKV - 1) / BKV;
+      if (it.q0 < it.qlen && it.klen > 0) { idx = i; c = 0; return valid = true; }
+    }
+    return valid = false;
+  }
+  __device__ __forceinline__ void init(const int* m, const dtts_attention_params& p, int qb, int first, int str) {
+    meta = m; n_utt = p.n_utt; n_heads = p.n_heads; qblocks = qb; stride = str;
+    load(first);
+  }
+  __device__ __forceinline__ void next() {           // advance one slot
+    if (++c >= it.nc) load(idx + stride);
+  }
+  __device__ __forceinline__ bool last_chunk() const { return c == it.nc - 1; }
+};
+
+// mbarrier wait without the clock reads of dtts_tc::mbar_wait (try_wait already suspends the thread for a
+// hardware-defined interval); a protocol bug still traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_lite(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 26)) {
+      printf("dtts attn_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const dtts_attention_params p, const int qblocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + SM_BAR);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* kv_full = bars + 4;            // [NS]
+  uint64_t* kv_empty = kv_full + NS;       // [NS]
+  uint64_t* s_full = kv_empty + NS;        // [NT][2]  (tile, S buffer)
+  uint64_t* p_full = s_full + 2 * NT;      // [NT]
+  uint64_t* o_full = p_full + NT;          // [NT]
+  uint32_t* tmem_slot = (uint32_t*)(o_full + NT);
+  int* meta = (int*)(smem + SM_META);      // [4][MAX_UTT]: q_off, q_len, k_off, k_len
+  float* sBiasAll = (float*)(smem + SM_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = p.bias_half;
+  const int nb = p.bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? 2 * half + 1 : 0;
+  const int bias_ld = nb + 2 * BIAS_PAD;   // per-head table (log2 domain) padded with its end values
+  const float LOG2E = 1.4426950408889634f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], NT); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NT); }
+    for (int t = 0; t < NT; ++t) { mbar_init(&s_full[2 * t], 1); mbar_init(&s_full[2 * t + 1], 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.n_utt; i += NTHREADS) {
+    meta[i] = p.q_off[i]; meta[MAX_UTT + i] = p.q_len[i]; meta[2 * MAX_UTT + i] = p.k_off[i]; meta[3 * MAX_UTT + i] = p.k_len[i];
+  }
+  for (int i = threadIdx.x; i < p.n_heads * bias_ld && nb; i += NTHREADS) {
+    const int h = i / bias_ld, j = i - h * bias_ld - BIAS_PAD;
+    sBiasAll[i] = p.bias_table[h * nb + min(max(j, 0), nb - 1)] * LOG2E;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmV) : "memory");
+      int stage = 0; uint32_t phase = 0, qphase[2] = {0, 0};
+      int qb = 0;
+      SlotIter sl;
+      sl.init(meta, p, qblocks, blockIdx.x, gridDim.x);
+      while (sl.valid) {
+        const Item& it = sl.it;
+        if (sl.c == 0) {
+          const int qrow = meta[it.b] + it.q0;
+          mbar_wait_lite(&q_empty[qb], qphase[qb] ^ 1);
+          mbar_expect_tx(&q_full[qb], NT * Q_TILE_BYTES);
+          for (int t = 0; t < NT; ++t)
+            tma_load_2d(smem + SM_Q + (qb * NT + t) * Q_TILE_BYTES, &tmQ, &q_full[qb], it.h * p.head_stride_q, qrow + t * BM);
+          qphase[qb] ^= 1;
+          qb ^= 1;
+        }
+        const int krow = meta[2 * MAX_UTT + it.b] + sl.c * BKV;
+        mbar_wait_lite(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = smem + SM_KV + stage * STAGE_BYTES;
+        mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
+        tma_load_2d(sk, &tmK, &kv_full[stage], it.h * p.head_stride_k, krow);
+        tma_load_2d(sk + KV_TILE_BYTES, &tmV, &kv_full[stage], it.h * p.head_stride_v, krow);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        sl.next();
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ MMA issuers (one warp per query tile) ========
+    // Tile t and slot g:  S_t(g) -> S buffer g&1;  P.V_t(g) reads P from buffer g&1 and accumulates into O_t.
+    // Issue order per tile: S_t(0), S_t(1), then for every slot g: wait P_t(g), P.V_t(g), S_t(g+2).  S_t(g+2) reuses
+    // the buffer P.V_t(g) has just read (same thread, in order), so the score MMA of the next chunk is never on the
+    // softmax warpgroup's critical path, and the three tiles never wait for each other.
+    if (lane == 0) {
+      const int t = warp - 1;
+      const uint32_t idesc_s = make_idesc(BM, BKV);                       // fp16 x fp16 -> fp32, both K-major
+      const uint32_t idesc_o = make_idesc(BM, HD) | (1u << 16);           // B (= V) MN-major
+      const uint64_t dq0 = make_desc(smem_u32(smem + SM_Q + t * Q_TILE_BYTES));        // + Q buffer, + k-step (>>4)
+      const uint64_t dk0 = make_desc(smem_u32(smem + SM_KV));                          // + stage, + k-step
+      const uint64_t dv0 = make_desc_mn(smem_u32(smem + SM_KV + KV_TILE_BYTES));       // + stage, + k-step
+      const uint32_t tm_s = tmem_base + TM_S + 2 * t * BKV, tm_o = tmem_base + TM_O + t * HD;
+      SlotIter pv, sn;                                                    // P.V cursor, S cursor (two slots ahead)
+      pv.init(meta, p, qblocks, blockIdx.x, gridDim.x);
+      sn = pv;
+      int s_stage = 0; uint32_t s_phase = 0; int s_buf = 0;               // ring position / S buffer of the S cursor
+      int qb = 0; uint32_t qbits = 0;                                     // Q buffer of the S cursor's item, q_full parities
+      int pv_stage = 0, pv_buf = 0;
+      uint32_t pf_phase = 0;
+      auto issue_s = [&]() {                                              // S_t for the S cursor's slot, then advance it
+        if (sn.c == 0) { mbar_wait_lite(&q_full[qb], (qbits >> qb) & 1u); qbits ^= 1u << qb; }
+        mbar_wait_lite(&kv_full[s_stage], s_phase);
+        tc_fence_after();
+        const uint64_t dq = dq0 + (uint64_t)((qb * NT * Q_TILE_BYTES) >> 4), dk = dk0 + (uint64_t)((s_stage * STAGE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tm_s + s_buf * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(&s_full[2 * t + s_buf]);
+        if (sn.last_chunk()) { tc_commit(&q_empty[qb]); qb ^= 1; }
+        if (++s_stage == NS) { s_stage = 0; s_phase ^= 1; }
+        s_buf ^= 1;
+        sn.next();
+      };
+      if (sn.valid) issue_s();
+      if (sn.valid) issue_s();
+      while (pv.valid) {
+        mbar_wait_lite(&p_full[t], pf_phase); pf_phase ^= 1;
+        tc_fence_after();
+        const uint64_t dv = dv0 + (uint64_t)((pv_stage * STAGE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_f16_ts(tm_o, tm_s + pv_buf * BKV + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (pv.c > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&o_full[t]);
+        tc_commit(&kv_empty[pv_stage]);                                   // 3 arrivals (one per tile) free the stage
+        if (sn.valid) issue_s();
+        if (++pv_stage == NS) pv_stage = 0;
+        pv_buf ^= 1;
+        pv.next();
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ softmax warpgroups ===========================
+    const int t = (warp - 4) >> 2;                 // query tile of this warpgroup
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;           // row within the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t to_addr = lane_addr + TM_O + t * HD;
+    const float sc2 = p.scale * LOG2E;
+    uint32_t sf_bits = 0, of_phase = 0;       // s_full parity of buffer u in bit u
+    int buf = 0;
+    bool first_slot = true;
+    // deferred epilogue of the previous item (its last P.V retires while the next item's first chunk is processed)
+    bool prev_store = false; float prev_inv = 0.f; long prev_row = 0; int prev_h = 0;
+    auto finish_prev = [&]() {                     // O_t / l -> fp16 rows (head-major [rows, n_heads*48])
+      float o[HD];
+      tmem_ld32_nowait(to_addr, o);
+      tmem_ld16(to_addr + 32, o + 32);
+      tmem_wait_ld();
+      if (prev_store) {
+        const float inv = prev_inv;
+        if (p.out_f16) {
+          uint4* op = reinterpret_cast<uint4*>((__half*)p.out_f16 + prev_row * p.ldo16 + prev_h * HD);
+#pragma unroll
+          for (int j = 0; j < HD; j += 8)
+            op[j / 8] = make_uint4(pack_h2(o[j] * inv, o[j + 1] * inv), pack_h2(o[j + 2] * inv, o[j + 3] * inv),
+                                   pack_h2(o[j + 4] * inv, o[j + 5] * inv), pack_h2(o[j + 6] * inv, o[j + 7] * inv));
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + prev_row * p.ldo32 + prev_h * HD);
+#pragma unroll
+          for (int j = 0; j < HD; j += 4) op[j / 4] = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+        }
+      }
+    };
+    bool prev_live = false;
+    SlotIter sl;
+    sl.init(meta, p, qblocks, blockIdx.x, gridDim.x);
+    float m_used = -INFINITY, l_run = 0.f;
+    while (sl.valid) {
+      const Item& it = sl.it;
+      const int c = sl.c, k0 = c * BKV;
+      const float* sBias = sBiasAll + it.h * bias_ld + BIAS_PAD;
+      const int qi = it.q0 + t * BM + row;                  // query index within the utterance
+      const bool warp_live = it.q0 + t * BM + quarter * 32 < it.qlen;
+      if (c == 0) { m_used = -INFINITY; l_run = 0.f; }
+      const uint32_t ts_addr = lane_addr + TM_S + (2 * t + buf) * BKV;
+      mbar_wait_lite(&s_full[2 * t + buf], (sf_bits >> buf) & 1u); sf_bits ^= 1u << buf;
+      tc_fence_after();
+      float corr = 1.f;
+      bool need_rescale = false;
+      if (warp_live) {
+        float s[BKV];
+        tmem_ld32_nowait(ts_addr, s);
+        tmem_ld16(ts_addr + 32, s + 32);
+        tmem_wait_ld();
+        // scores in the log2 domain: s*scale*log2e + bias*log2e
+        if (nb) {
+          int base = k0 - qi + half;                        // table index of column 0
+          const bool cst = __all_sync(0xffffffffu, base >= 2 * half || base + BKV - 1 <= 0);
+          if (cst) {
+            const float ub = base >= 2 * half ? sBias[2 * half] : sBias[0];
+#pragma unroll
+            for (int j = 0; j < BKV; ++j) s[j] = fmaf(s[j], sc2, ub);
+          } else {
+            base = min(max(base, -BIAS_PAD), 2 * half + 1);
+            const float* bp = sBias + base;
+#pragma unroll
+            for (int j = 0; j < BKV; ++j) s[j] = fmaf(s[j], sc2, bp[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BKV; ++j) s[j] *= sc2;
+        }
+        if (k0 + BKV > it.klen) {
+#pragma unroll
+          for (int j = 0; j < BKV; ++j)
+            if (k0 + j >= it.klen) s[j] = -INFINITY;
+        }
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+        for (int j = 4; j < BKV; j += 4) {
+          mx0 = fmaxf(mx0, s[j]); mx1 = fmaxf(mx1, s[j + 1]); mx2 = fmaxf(mx2, s[j + 2]); mx3 = fmaxf(mx3, s[j + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (c == 0) {
+          m_used = mx;
+        } else if (mx > m_used + RESCALE_THRESHOLD) {
+          corr = ex2f(m_used - mx);
+          m_used = mx;
+          need_rescale = true;
+        }
+        uint32_t pk[BKV / 2];
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < BKV; j += 2) {
+          const float p0 = ex2f(s[j] - m_used), p1 = ex2f(s[j + 1] - m_used);
+          l0 += p0; l1 += p1;
+          pk[j / 2] = pack_h2(p0, p1);
+        }
+        l_run = l_run * corr + (l0 + l1);
+        // P (fp16, 24 columns) overwrites the head of this S buffer; the tensor core reads it as the A operand of P.V
+        tmem_st16(ts_addr, pk);
+        tmem_st8(ts_addr + 16, pk + 16);
+      }
+      if (!first_slot) {
+        // P.V of the previous slot: retired long ago in steady state (it was issued before this slot's scores were read)
+        mbar_wait_lite(&o_full[t], of_phase); of_phase ^= 1;
+        tc_fence_after();
+        if (c == 0) {
+          if (prev_live) finish_prev();                       // previous item: O is complete, and P.V_t(c=0) will overwrite it
+        } else if (__any_sync(0xffffffffu, need_rescale)) {
+          float o[HD];
+          tmem_ld32_nowait(to_addr, o);
+          tmem_ld16(to_addr + 32, o + 32);
+          tmem_wait_ld();
+          uint32_t ob[HD];
+#pragma unroll
+          for (int j = 0; j < HD; ++j) ob[j] = __float_as_uint(o[j] * corr);
+          tmem_st32(to_addr, ob);
+          tmem_st16(to_addr + 32, ob + 32);
+        }
+      }
+      first_slot = false;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (sl.last_chunk()) {                                  // remember what the deferred epilogue needs
+        prev_live = warp_live;
+        prev_store = warp_live && qi < it.qlen;
+        prev_inv = 1.0f / l_run;
+        prev_row = (long)(p.o_off ? p.o_off[it.b] : meta[it.b]) + qi;
+        prev_h = it.h;
+      }
+      buf ^= 1;
+      sl.next();
+    }
+    if (!first_slot) {
+      mbar_wait_lite(&o_full[t], of_phase);
+      tc_fence_after();
+      if (prev_live) finish_prev();
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+extern "C" int dtts_attention_f16_tc(const dtts_attention_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->q && p->k && p->v && p->q_off && p->q_len && p->k_off && p->k_len, "attention_f16_tc: null argument");
+  DTTS_REQUIRE(p->is_f16 && p->head_dim == HD, "attention_f16_tc: needs fp16 operands and head_dim 48");
+  DTTS_REQUIRE(!p->causal, "attention_f16_tc: causal masks are not supported (use dtts_attention_f32)");
+  DTTS_REQUIRE(p->bias_mode == DTTS_ATTN_BIAS_NONE || (p->bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE && p->bias_table),
+               "attention_f16_tc: unsupported bias mode");
+  const int bias_floats = p->bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? p->n_heads * (2 * p->bias_half + 1 + 2 * BIAS_PAD) : 0;
+  // shapes beyond the shared-memory staging limits run on the mma.sync kernel (same contract)
+  if (p->n_utt > MAX_UTT || bias_floats > BIAS_MAX_FLOATS) return dtts_attention_f16_flash(p, stream);
+  const int smem_bytes = SM_BIAS + bias_floats * 4 + 1024;
+  DTTS_REQUIRE(p->n_rows > 0, "attention_f16_tc: n_rows (rows of the q/k/v buffers) must be set");
+  DTTS_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldv % 8 == 0 && p->head_stride_q % 8 == 0 && p->head_stride_k % 8 == 0 && p->head_stride_v % 8 == 0,
+               "attention_f16_tc: strides must keep 16-byte alignment");
+  DTTS_REQUIRE((((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v) & 15) == 0, "attention_f16_tc: operands must be 16-byte aligned");
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "attention_f16_tc: no output");
+  DTTS_REQUIRE(!p->out_f16 || (p->ldo16 % 8 == 0 && (((uintptr_t)p->out_f16) & 15) == 0), "attention_f16_tc: fp16 output must be 16-byte aligned");
+  DTTS_REQUIRE(!p->out_f32 || (p->ldo32 % 4 == 0 && (((uintptr_t)p->out_f32) & 15) == 0), "attention_f16_tc: fp32 output must be 16-byte aligned");
+  if (p->n_utt <= 0 || p->max_q_len <= 0) return 0;
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) DTTS_FAIL(-6, "attention_f16_tc: no CUDA device");
+    cudaError_t e = cudaFuncSetAttribute(flash48_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e != cudaSuccess) { g_sms = 0; DTTS_FAIL(-3, "cudaFuncSetAttribute(flash48_tc): %s", cudaGetErrorString(e)); }
+  }
+  // 64-column boxes over the 48-wide heads: the map ends at the last head's last element, so the 16 extra columns of
+  // the last head are zero-filled instead of read past the row
+  const int cols_q = (p->n_heads - 1) * p->head_stride_q + HD, cols_k = (p->n_heads - 1) * p->head_stride_k + HD,
+            cols_v = (p->n_heads - 1) * p->head_stride_v + HD;
+  CUtensorMap mq, mk, mv;
+  int rc = get_map(p->q, p->n_rows, cols_q, p->ldq, BM, &mq, 2);
+  if (rc) return rc;
+  rc = get_map(p->k, p->n_rows, cols_k, p->ldk, BKV, &mk, 2);
+  if (rc) return rc;
+  rc = get_map(p->v, p->n_rows, cols_v, p->ldv, BKV, &mv, 2);
+  if (rc) return rc;
+  const int qblocks = ceil_div(p->max_q_len, NT * BM);
+  const long items = (long)p->n_utt * p->n_heads * qblocks;
+  const int grid = items < g_sms ? (int)items : g_sms;
+  flash48_tc_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(mq, mk, mv, *p, qblocks);
+  DTTS_CHECK_LAUNCH("attention_f16_tc");
+  return 0;
+}

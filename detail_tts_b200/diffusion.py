@@ -16,6 +16,7 @@ sampler update are fp32; GEMM operands are fp16 with fp32 accumulation (SURVEY.m
 the 1e-3 mel budget, fp16 passes).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,8 @@ from . import ops, pack
 from .ops import RowsLayout
 
 MODEL_CH, HEADS, IN_CH, OUT_CH = 768, 16, 128, 256
+FLASH_IMPL = os.environ.get("DTTS_FLASH", "tc")     # "tc": tcgen05 kernel (attn_tc.cu); "mma": mma.sync kernel (attn_flash.cu)
+FLASH_IMPL = True if FLASH_IMPL == "mma" else "tc"
 F16 = torch.float16
 
 
@@ -111,7 +114,7 @@ class DiffusionTts:
         ops.gemm(buf.g, at.qkv, out16=buf.qkv, row_utt=ru)
         ops.attention(buf.qkv, buf.qkv[:, ch:], buf.qkv[:, 2 * ch:], HEADS, ch, lay.off, lay.len, lay.off, lay.len,
                       lay.max_len, lay.max_len, ch ** -0.5, out16=buf.a, head_stride=3 * ch, bias_table=at.bias,
-                      bias_half=64, flash=(ch == 48))
+                      bias_half=64, flash=FLASH_IMPL if ch == 48 else False)
         ops.gemm(buf.a, at.proj, res=x32, out32=x32, out16=out16, row_utt=ru)
 
     def _res_block(self, rb, x_in, x_out, lay, buf, film, film_idx):

@@ -112,7 +112,8 @@ def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max
     L = _lib.lib()
     hs = head_dim if head_stride is None else head_stride
     mode = BIAS_RELPOS_TABLE if bias_table is not None else (BIAS_WINDOW_REL if rel_k is not None else BIAS_NONE)
-    L.call("dtts_attention_f16_flash" if flash else "dtts_attention_f32", q=q, k=k, v=v,
+    fn = {False: "dtts_attention_f32", True: "dtts_attention_f16_flash", "tc": "dtts_attention_f16_tc"}[flash]
+    L.call(fn, q=q, k=k, v=v, n_rows=q.shape[0],
            is_f16=int(q.dtype == torch.float16), ldq=_ld(q), ldk=_ld(k), ldv=_ld(v), head_stride_q=hs,
            head_stride_k=hs, head_stride_v=hs, n_utt=q_off.numel(), n_heads=n_heads, head_dim=head_dim,
            q_off=q_off, q_len=q_len, k_off=k_off, k_len=k_len, max_q_len=max_q, max_k_len=max_k,

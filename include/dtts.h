@@ -122,6 +122,7 @@ typedef struct {
   float* out_f32; int ldo32; void* out_f16; int ldo16;  /* [rows, n_heads*head_dim] head-major */
   const int* o_off;           /* [n_utt] first output row of utterance b; NULL = q_off */
   float* out_lo; int ldo_lo;  /* decode fast path only: out_f32 receives the tf32-exact high part, out_lo the low part */
+  int n_rows;                 /* dtts_attention_f16_tc only: rows of the q / k / v buffers (bounds of the TMA tensor maps) */
 } dtts_attention_params;
 /* softmax(scale*q.k + bias) v in exact fp32 on CUDA cores, one query per CTA.  Covers the small
  * attentions: GPT-2 causal attention incl. KV-cache decode (modeling_gpt2.py:54-72),
@@ -132,6 +133,10 @@ int dtts_attention_f32(const dtts_attention_params* p, void* stream);
  * AttentionBlock hot loop: vqvae/utils/diff_util.py:145-169 + xtransformers.py:177-186.
  * Requires is_f16, head_dim 48, bias_mode NONE or RELPOS_TABLE, non-causal. */
 int dtts_attention_f16_flash(const dtts_attention_params* p, void* stream);
+/* Same contract on the 5th-generation tensor cores: persistent warp-specialised tcgen05 kernel, S and O accumulators
+ * in TMEM, P fed back to the tensor core from TMEM, K/V chunks through a TMA ring, one softmax thread per query row.
+ * Additionally requires n_rows and 16-byte aligned outputs. */
+int dtts_attention_f16_tc(const dtts_attention_params* p, void* stream);
 
 typedef struct {
   const float* logits; int ldl; int n_rows, vocab;

@@ -283,7 +283,7 @@ def _bias_table(wt, half, scale):
     return relpos_table(wt, half, scale)
 
 
-@pytest.mark.parametrize("lens", [[280, 64, 1, 129], [70]])
+@pytest.mark.parametrize("lens", [[280, 64, 1, 129], [70], [500, 97, 385], [280] * 40])
 def test_attention_flash_vs_f32(dlib, lens):
     """Diffusion AttentionBlock layout: per head q,k,v contiguous (144 ch), relpos bias table."""
     H, hd = 16, 48
@@ -294,6 +294,7 @@ def test_attention_flash_vs_f32(dlib, lens):
     wt = torch.randn(32, H, generator=g, device=DEV) * 0.3
     table = _bias_table(wt, 64, math.sqrt(hd))
     o_flash = torch.zeros(M, H * hd, device=DEV, dtype=torch.float16)
+    o_tc = torch.zeros(M, H * hd, device=DEV, dtype=torch.float16)
     o_simt = torch.zeros(M, H * hd, device=DEV)
     common = dict(is_f16=1, ldq=3 * H * hd, ldk=3 * H * hd, ldv=3 * H * hd, head_stride_q=3 * hd, head_stride_k=3 * hd,
                   head_stride_v=3 * hd, n_utt=len(lens), n_heads=H, head_dim=hd, q_off=off, q_len=ln, k_off=off, k_len=ln,
@@ -301,7 +302,12 @@ def test_attention_flash_vs_f32(dlib, lens):
                   bias_table=table, bias_half=64)
     dlib.call("dtts_attention_f16_flash", q=qkv16, k=qkv16[:, hd:], v=qkv16[:, 2 * hd:], out_f16=o_flash, ldo16=H * hd, **common)
     dlib.call("dtts_attention_f32", q=qkv16, k=qkv16[:, hd:], v=qkv16[:, 2 * hd:], out_f32=o_simt, ldo32=H * hd, **common)
-    for b, n in enumerate(lens):
+    for _ in range(2):   # twice: the persistent tcgen05 kernel must leave no state behind
+        o_tc.zero_()
+        dlib.call("dtts_attention_f16_tc", q=qkv16, k=qkv16[:, hd:], v=qkv16[:, 2 * hd:], out_f16=o_tc, ldo16=H * hd, n_rows=M,
+                  **common)
+    torch.cuda.synchronize()
+    for b, n in enumerate(lens[:6]):
         sl = slice(int(off[b]), int(off[b]) + n)
         blk = qkv16[sl].float().reshape(n, H, 3, hd)
         q, k, v = (blk[:, :, i].permute(1, 0, 2) for i in range(3))
@@ -311,6 +317,13 @@ def test_attention_flash_vs_f32(dlib, lens):
         r = _attn_ref(q, k, v, hd ** -0.5, bias=bias).permute(1, 0, 2).reshape(n, H * hd)
         assert (o_simt[sl].double() - r).abs().max().item() < 2e-5
         assert (o_flash[sl].double() - r).abs().max().item() < 4e-3
+        assert (o_tc[sl].double() - r).abs().max().item() < 4e-3, (b, n)
+    # every utterance of the batch against the mma.sync kernel; separator rows untouched
+    valid = torch.zeros(M, dtype=torch.bool, device=DEV)
+    for b, n in enumerate(lens):
+        valid[int(off[b]):int(off[b]) + n] = True
+    assert (o_tc[valid].float() - o_flash[valid].float()).abs().max().item() < 4e-3
+    assert o_tc[~valid].abs().max().item() == 0 if (~valid).any() else True
 
 
 def test_process_logits_and_append(dlib):
