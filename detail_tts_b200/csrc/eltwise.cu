@@ -348,5 +348,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_rows2bct_params); SZ(dtts_eltwise_params); SZ(dtts_embed_params); SZ(dtts_repeat_rows_params);
   SZ(dtts_mean_rows_params); SZ(dtts_tsemb_params); SZ(dtts_couple_params); SZ(dtts_zp_params);
   SZ(dtts_rowutt_params); SZ(dtts_copy_utts_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
+  SZ(dtts_voc_mrf_params); SZ(dtts_conv_post_params);
   return -1;
 }

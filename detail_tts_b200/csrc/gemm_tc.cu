@@ -303,16 +303,16 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows, esize;
+  const void* ptr; int rows, cols, ld, box_rows, esize, box_cols;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && esize == o.esize;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && esize == o.esize && box_cols == o.box_cols;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.ptr;
     h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box_rows; h = h * 1000003u ^ (size_t)k.esize;
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box_rows; h = h * 1000003u ^ (size_t)k.esize; h = h * 1000003u ^ (size_t)k.box_cols;
     return h;
   }
 };
@@ -389,7 +389,13 @@ int common_checks(const dtts_gemm_params* p, const char* who, int ld_mult) {
 // 2D tensor map (fp16: esize 2, fp32: esize 4) over a row-major [rows, cols] matrix (ld elements),
 // box [box_rows, 128 bytes], 128B swizzle.
 int dtts_tc::get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int esize) {
-  MapKey key{ptr, rows, cols, ld, box_rows, esize};
+  return get_map_ex(ptr, rows, cols, ld, box_rows, 0, out, esize);
+}
+
+// box_cols == 0: box [box_rows, 128 bytes] with 128B swizzle (tcgen05 operand tiles); otherwise a plain
+// [box_rows, box_cols] box without swizzle (rows land contiguously in shared memory).
+int dtts_tc::get_map_ex(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out, int esize) {
+  MapKey key{ptr, rows, cols, ld, box_rows, esize, box_cols};
   {
     std::lock_guard<std::mutex> g(g_maps_mu);
     auto it = g_maps.find(key);
@@ -399,10 +405,10 @@ int dtts_tc::get_map(const void* ptr, int rows, int cols, int ld, int box_rows, 
   if (!fn) DTTS_FAIL(-4, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * esize};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : 128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     DTTS_FAIL(-5, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box_rows=%d ptr=%p", (int)r, rows, cols, ld, box_rows, ptr);
@@ -419,6 +425,9 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->N;
+  static int bn256 = -1;   // 256-wide tiles (less shared-memory read traffic per MMA): +5 % on the diffusion shapes
+  if (bn256 < 0) { const char* e = getenv("DTTS_GEMM_BN256"); bn256 = e ? atoi(e) : 1; }
+  if (bn256 && N % 256 == 0) return launch<256, false>(p, st);
   if (N % 192 == 0) return launch<192, false>(p, st);
   if (N > 64) return launch<128, false>(p, st);
   if (N > 32) return launch<64, false>(p, st);

@@ -5,7 +5,10 @@
 // GroupNorm is HBM/L2-bound: one CTA owns (utterance, 4 groups); the strip is read once from
 // global into shared memory (when it fits), statistics are two-pass exact (mean, then centred
 // variance) and the normalised fp16 GEMM operand is written straight from shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace {
 
@@ -284,6 +287,136 @@ groupnorm_reg_kernel(const T* __restrict__ x, int ldx, int cpg, const int* __res
   }
 }
 
+// TMA-staged persistent variant (the diffusion hot loop): the kernel is HBM-bound, so what matters is that a
+// full strip is always in flight per SM.  One CTA loops over (utterance, channel strip) items; the strip
+// [T, 192 bytes] is brought into shared memory by TMA (32-row boxes, mbarrier completion) one item AHEAD of the
+// one being normalised, the three passes (sum, centred sum of squares, normalise + FiLM + SiLU) read shared
+// memory, and the fp16 GEMM operand is written straight to HBM.  Rows land contiguously in shared memory, so
+// thread i reads vector i, i + 384, ...: conflict-free and the channel column of a thread is fixed.
+constexpr int GNT_BOX_ROWS = 32, GNT_STAGES = 2, GNT_ROW_BYTES = 192, GNT_MAX_SMEM = 224 * 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(GNR_THREADS, 2)
+groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, int n_gx, int n_utt, int stage_rows,
+                     const int* __restrict__ utt_off, const int* __restrict__ utt_len, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ film_scale, const float* __restrict__ film_shift,
+                     int ld_film, const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
+                     __half* __restrict__ out16, int ldo16) {
+  using namespace dtts_tc;
+  typedef typename GnVec<T>::Raw Raw;
+  extern __shared__ uint8_t gn_smem_raw[];
+  uint8_t* smem = gn_smem_raw + ((128u - (smem_u32(gn_smem_raw) & 127u)) & 127u);
+  uint64_t* full = (uint64_t*)smem;                        // [GNT_STAGES]
+  uint8_t* bufs = smem + 128;
+  __shared__ float red[GNR_THREADS / 32][GNR_MAXG];
+  const int stage_bytes = stage_rows * GNT_ROW_BYTES;
+  const int cw = gpc * cpg;                                // channels per strip: cw * sizeof(T) == 192
+  const int Q = cw >> 2;                                   // 4-channel vectors per row (12 or 24)
+  const int rs = GNR_THREADS / Q;                          // rows per sweep of the CTA
+  const int col = threadIdx.x % Q, rsub = threadIdx.x / Q;
+  const int g = (col * 4) / cpg;
+  const int n_items = n_utt * n_gx;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GNT_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int item, int stage) {                  // thread 0 only
+    const int b = item / n_gx, gx = item - b * n_gx;
+    const int T_ = utt_len[b], row0 = utt_off[b];
+    const int nbox = (T_ + GNT_BOX_ROWS - 1) / GNT_BOX_ROWS;
+    uint8_t* dst = bufs + stage * stage_bytes;
+    mbar_expect_tx(&full[stage], nbox * GNT_BOX_ROWS * GNT_ROW_BYTES);
+    for (int i = 0; i < nbox; ++i)
+      tma_load_2d(dst + i * GNT_BOX_ROWS * GNT_ROW_BYTES, &tm, &full[stage], gx * cw, row0 + i * GNT_BOX_ROWS);
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm) : "memory");
+    for (int s = 0; s < GNT_STAGES; ++s) {
+      const int item = blockIdx.x + s * gridDim.x;
+      if (item < n_items) issue(item, s);
+    }
+  }
+  int it = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const int stage = it % GNT_STAGES;
+    const uint32_t phase = (it / GNT_STAGES) & 1;
+    const int b = item / n_gx, gx = item - b * n_gx;
+    const int T_ = utt_len[b];
+    const long row0 = utt_off[b];
+    const int c = gx * cw + col * 4;
+    const int nvec = T_ * Q;
+    const Raw* buf = reinterpret_cast<const Raw*>(bufs + stage * stage_bytes);
+    mbar_wait(&full[stage], phase);
+    float s = 0.f;
+    for (int e = threadIdx.x; e < nvec; e += GNR_THREADS) {
+      float f[4];
+      GnVec<T>::unpack(buf[e], f);
+      s += (f[0] + f[1]) + (f[2] + f[3]);
+    }
+    const float inv_n = 1.0f / ((float)T_ * cpg);
+    float sg[GNR_MAXG];
+#pragma unroll
+    for (int i = 0; i < GNR_MAXG; ++i) sg[i] = g == i ? s : 0.f;
+    block_sum_g<GNR_MAXG>(sg, red);
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < GNR_MAXG; ++i) mean = g == i ? sg[i] * inv_n : mean;
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < nvec; e += GNR_THREADS) {
+      float f[4];
+      GnVec<T>::unpack(buf[e], f);
+      const float a0 = f[0] - mean, a1 = f[1] - mean, a2 = f[2] - mean, a3 = f[3] - mean;
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+#pragma unroll
+    for (int i = 0; i < GNR_MAXG; ++i) sg[i] = g == i ? ss : 0.f;
+    block_sum_g<GNR_MAXG>(sg, red);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < GNR_MAXG; ++i) var = g == i ? sg[i] * inv_n : var;
+    const float rstd = rsqrtf(var + eps);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float A_[4] = {rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w};
+    float B_[4] = {be.x - mean * A_[0], be.y - mean * A_[1], be.z - mean * A_[2], be.w - mean * A_[3]};
+    if (film_scale) {   // (x*A+B)*(1+fs)+fb = x*A(1+fs) + B(1+fs)+fb
+      const long fr = film_idx ? film_idx[b] : b;
+      const float4 fs = *reinterpret_cast<const float4*>(film_scale + fr * ld_film + c);
+      const float4 fb = *reinterpret_cast<const float4*>(film_shift + fr * ld_film + c);
+      const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { A_[q] *= f1[q]; B_[q] = B_[q] * f1[q] + f0[q]; }
+    }
+    {
+      float* o32 = out32 ? out32 + (row0 + rsub) * ldo32 + c : nullptr;
+      __half* o16 = out16 ? out16 + (row0 + rsub) * ldo16 + c : nullptr;
+      const long s32 = (long)rs * ldo32, s16 = (long)rs * ldo16;
+      for (int e = threadIdx.x; e < nvec; e += GNR_THREADS) {
+        float y[4];
+        GnVec<T>::unpack(buf[e], y);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = fmaf(y[q], A_[q], B_[q]);
+        if (act == DTTS_ACT_SILU) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) y[q] = silu_fast(y[q]);
+        }
+        if (o32) { *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]); o32 += s32; }
+        if (o16) {
+          __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+          *reinterpret_cast<uint2*>(o16) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          o16 += s16;
+        }
+      }
+    }
+    __syncthreads();                                         // every thread is done with this stage's buffer
+    if (threadIdx.x == 0) {
+      const int nxt = item + GNT_STAGES * gridDim.x;
+      if (nxt < n_items) issue(nxt, stage);
+    }
+  }
+}
+
 constexpr int LN_MAXE = 32;  // C <= 1024
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
@@ -345,6 +478,50 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
     cudaFuncSetAttribute(groupnorm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   }
   cudaStream_t st0 = (cudaStream_t)stream;
+  {
+    // TMA-staged persistent path (see groupnorm_tma_kernel): strips of exactly 192 bytes per row
+    const int es = p->x_is_f16 ? 2 : 4;
+    const int gpc = cpg * es <= GNT_ROW_BYTES ? GNT_ROW_BYTES / (cpg * es) : 0;
+    const int stage_rows = (p->max_len + GNT_BOX_ROWS - 1) / GNT_BOX_ROWS * GNT_BOX_ROWS;
+    const size_t smem = 128 + 128 + (size_t)GNT_STAGES * stage_rows * GNT_ROW_BYTES;
+    static int tma_on = -1, sms = 0;
+    if (tma_on < 0) {
+      const char* e = getenv("DTTS_GN_TMA");
+      tma_on = e ? atoi(e) : 0;   // measured on B200 (B=128, F=280): 90.7 / 81.3 us vs 84.7 / 80.2 us for the register path
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      // (static shared memory counts against the 227 KB limit too)
+      cudaError_t e1 = cudaFuncSetAttribute(groupnorm_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM);
+      cudaError_t e2 = cudaFuncSetAttribute(groupnorm_tma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); tma_on = 0; }
+    }
+    const bool aligned = ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->x)) & 15) == 0 && (p->ldx * es) % 16 == 0 &&
+                         (!p->film_scale || (((((uintptr_t)p->film_scale) | ((uintptr_t)p->film_shift)) & 15) == 0 && p->ld_film % 4 == 0)) &&
+                         (!p->out_f32 || ((((uintptr_t)p->out_f32) & 15) == 0 && p->ldo32 % 4 == 0)) &&
+                         (!p->out_f16 || ((((uintptr_t)p->out_f16) & 7) == 0 && p->ldo16 % 4 == 0));
+    if (tma_on && sms > 0 && p->n_rows > 0 && p->max_len > 0 && gpc >= 1 && gpc <= GNR_MAXG && gpc * cpg * es == GNT_ROW_BYTES &&
+        p->groups % gpc == 0 && cpg % 4 == 0 && aligned && smem <= (size_t)GNT_MAX_SMEM) {
+      CUtensorMap tm;
+      const int cw = gpc * cpg;
+      int rc = dtts_tc::get_map_ex(p->x, p->n_rows, p->C, p->ldx, GNT_BOX_ROWS, cw, &tm, es);
+      if (rc) return rc;
+      const int n_gx = p->groups / gpc;
+      const long items = (long)p->n_utt * n_gx;
+      const int per_sm = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
+      const int grid = items < (long)per_sm * sms ? (int)items : per_sm * sms;
+      if (p->x_is_f16)
+        groupnorm_tma_kernel<__half><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, p->utt_off, p->utt_len,
+            p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32,
+            (__half*)p->out_f16, p->ldo16);
+      else
+        groupnorm_tma_kernel<float><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, p->utt_off, p->utt_len,
+            p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32,
+            (__half*)p->out_f16, p->ldo16);
+      DTTS_CHECK_LAUNCH("groupnorm_tma");
+      return 0;
+    }
+  }
   {
     // register-resident fast path (see groupnorm_reg_kernel)
     const int ve = 4, gpc = p->x_is_f16 ? 4 : 2, maxr = p->x_is_f16 ? GnVec<__half>::MAXR : GnVec<float>::MAXR;

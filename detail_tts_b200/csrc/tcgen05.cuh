@@ -101,5 +101,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // tensor-map cache (host): 2D map over a row-major [rows, cols] matrix (ld elements), box [box_rows, 128 bytes],
 // 128B swizzle; esize 2 = fp16, 4 = fp32.  Defined in gemm_tc.cu.
 int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int esize = 2);
+// box_cols > 0: plain [box_rows, box_cols] box without swizzle
+int get_map_ex(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out, int esize);
 
 }  // namespace dtts_tc

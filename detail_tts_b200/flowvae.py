@@ -12,6 +12,7 @@ fp16 operand, so no standalone elementwise pass touches HBM; ConvTranspose1d is 
 writes the upsampled rows in place.  Residual streams are fp32, GEMM operands fp16.
 """
 import math
+import os
 
 import torch
 
@@ -25,6 +26,7 @@ UPS = ((8, 16), (4, 8), (2, 2), (2, 2), (2, 2))     # (stride, kernel)   config_
 RB_K = (3, 7, 11)
 RB_D = (1, 3, 5)
 GAP = 4   # separator rows at frame rate: conv_pre k7 needs 3; x8 upsampling gives >= 25 for k11 d5
+FUSED_MRF = os.environ.get("DTTS_VOC_FUSED", "1") != "0"   # narrow stages (<= 32 padded channels): csrc/voc_fused.cu
 
 
 def _wn(W, p):
@@ -150,7 +152,7 @@ class Generator:
         # cond(g) + conv_pre bias as one per-utterance bias (fp32 GEMV)
         self.cond = pack.pack_linear(W[p + "cond.weight"], W[p + "cond.bias"] + W[p + "conv_pre.bias"], torch.float32, device)
         self.c0 = self.conv_pre.N
-        self.ups, self.res, self.cp = [], [], []
+        self.ups, self.res, self.cp, self.mrf = [], [], [], []
         ch = self.c0
         for i, (u, k) in enumerate(UPS):
             w = _wn(W, p + f"ups.{i}.")                         # [Cin, Cout, k]
@@ -167,8 +169,19 @@ class Generator:
                                        padding=(rk - 1) // 2, n_pad=8) for m in range(3)]
                 blocks.append((c1, c2))
             self.res.append(blocks)
+            # fused multi-receptive-field kernel for the narrow stages: all 18 convs as B fragments
+            self.mrf.append(None)
+            if cp <= 32:
+                convs = []
+                for j in range(3):
+                    q = p + f"resblocks.{i * 3 + j}."
+                    for m in range(3):
+                        convs.append((_wn(W, q + f"convs1.{m}."), W[q + f"convs1.{m}.bias"]))
+                        convs.append((_wn(W, q + f"convs2.{m}."), W[q + f"convs2.{m}.bias"]))
+                self.mrf[-1] = pack.pack_mrf_fragments(convs, 16 if cp <= 16 else 32, device)
             ch = cout
         self.conv_post = pack.pack_conv1d(W[p + "conv_post.weight"], None, F16, device, padding=3)
+        self.conv_post_w = W[p + "conv_post.weight"][0].t().to(device=device, dtype=torch.float32).contiguous()   # [7, 12]
 
     def forward_rows(self, z16, g, lay):
         """z16 rows [M,192] fp16, g [B,768] fp32 or None -> (wav rows [M*256, 1] fp32, layout x256)."""
@@ -189,13 +202,22 @@ class Generator:
             cp = self.cp[i]
             nxt = cur.scaled(u)
             z = lambda d: torch.zeros(nxt.M, cp, dtype=d, device=dev)  # noqa: E731
+            last_slope = LRELU_SLOPE if i < len(UPS) - 1 else 0.01      # F.leaky_relu default, model_24k.py:284
+            ru = nxt.row_utt
+            if FUSED_MRF and self.mrf[i] is not None:
+                # ConvTranspose1d (polyphase GEMM) -> fp32 x; then ONE launch for the 18 convs of the three ResBlocks
+                x32, xs16 = z(torch.float32), z(F16)
+                ops.gemm(x16, self.ups[i], out32=x32.view(cur.M, u * cp), row_utt=cur.row_utt)
+                wf, bias = self.mrf[i]
+                ops._lib.lib().call("dtts_voc_mrf", x=x32, ldx=cp, M=nxt.M, Cp=cp, row_utt=ru, w_frag=wf, bias=bias,
+                                    slope=LRELU_SLOPE, slope_out=last_slope, out_f16=xs16, ldo16=cp)
+                x16, cur = xs16, nxt
+                continue
             x32, xl16 = z(torch.float32), z(F16)
             # polyphase ConvTranspose1d: row t of the GEMM output holds the u upsampled rows t*u..t*u+u-1
             ops.gemm(x16, self.ups[i], out32=x32.view(cur.M, u * cp), out16=xl16.view(cur.M, u * cp),
                      act16=ops.ACT_LRELU, act16_param=LRELU_SLOPE, row_utt=cur.row_utt)
-            ru = nxt.row_utt
             xs32, xs16, t16, xk32, xk16 = z(torch.float32), z(F16), z(F16), z(torch.float32), z(F16)
-            last_slope = LRELU_SLOPE if i < len(UPS) - 1 else 0.01      # F.leaky_relu default, model_24k.py:284
             for j, (c1, c2) in enumerate(self.res[i]):
                 src32, src16 = x32, xl16
                 for m in range(3):
@@ -209,7 +231,11 @@ class Generator:
                                  accumulate=j > 0, act16=ops.ACT_LRELU, act16_param=last_slope, row_utt=ru)
             x16, cur = xs16, nxt
         wav = torch.zeros(cur.M, 1, dtype=torch.float32, device=dev)
-        ops.gemm(x16, self.conv_post, out32=wav, act=ops.ACT_TANH, row_utt=cur.row_utt, bias=False)
+        if FUSED_MRF and x16.shape[1] == 16:
+            ops._lib.lib().call("dtts_conv_post", x=x16, ldx=16, M=cur.M, C=self.conv_post_w.shape[1], row_utt=cur.row_utt,
+                                w=self.conv_post_w, out=wav, ldo=1)
+        else:
+            ops.gemm(x16, self.conv_post, out32=wav, act=ops.ACT_TANH, row_utt=cur.row_utt, bias=False)
         return wav, cur
 
     @torch.no_grad()

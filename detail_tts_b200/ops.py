@@ -95,7 +95,7 @@ def groupnorm(x, lay, gamma, beta, out32=None, out16=None, groups=32, film=None,
                     film_scale=film, film_shift=film[:, C:] if film is not None else None,
                     ld_film=_ld(film) if film is not None else 0, film_idx=film_idx, act=act, eps=eps,
                     out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
-                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0)
+                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, n_rows=x.shape[0])
 
 
 def layernorm(x, gamma, beta, out32=None, out16=None, res=None, M=None, eps=1e-5, ldo32=None, row_utt=None):

@@ -155,3 +155,22 @@ def pack_linear_tf32x3(w, b, device, n_pad=1):
     hi, lo = split_tf32_host(pw.w)
     pw.w, pw.w_lo = hi.contiguous(), lo.contiguous()
     return pw
+
+
+def pack_mrf_fragments(convs, cp, device):
+    """[(w [C, C, k] fp32 (weight-norm folded), bias [C])] x 18 in dtts_voc_mrf order -> (w_frag uint8 tensor, bias [18, cp]).
+    Per conv the fp16 weights are laid out as mma.sync m16n8k16 B fragments [tap][cp/8][cp/16][lane][4]:
+    lane = g*4 + tig holds W[tap][n = nt*8 + g][k = ks*16 + 2*tig + {0, 1, 8, 9}]  (n = output channel, k = input channel)."""
+    NT, KS = cp // 8, cp // 16
+    frags, biases = [], []
+    for w, b in convs:
+        C_out, C_in, k = w.shape
+        Wp = torch.zeros(k, cp, cp, dtype=torch.float32)
+        Wp[:, :C_out, :C_in] = w.permute(2, 0, 1).float().cpu()
+        f = Wp.view(k, NT, 8, KS, 2, 4, 2).permute(0, 1, 3, 2, 5, 4, 6).contiguous()   # tap, nt, ks, g, tig, hh, e
+        frags.append(f.reshape(-1).to(torch.float16))
+        bb = torch.zeros(cp)
+        bb[:C_out] = b.float().cpu()
+        biases.append(bb)
+    wf = torch.cat(frags).contiguous().to(device)
+    return wf, torch.stack(biases).contiguous().to(device)

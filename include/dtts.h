@@ -89,6 +89,7 @@ typedef struct {
   int act;                                  /* DTTS_ACT_NONE or DTTS_ACT_SILU */
   float eps;
   float* out_f32; int ldo32; void* out_f16; int ldo16;
+  int n_rows;                               /* rows of x (bounds of the TMA tensor map); 0 = unknown: no TMA staging */
 } dtts_groupnorm_params;
 /* GroupNorm32 (fp32 statistics over channels-in-group x frames of ONE utterance) + optional
  * timestep FiLM + SiLU: vqvae/utils/diff_util.py:113-133, vqvae/diff_model.py:107,113-115,242. */
@@ -178,6 +179,33 @@ typedef struct {
 /* One ancestral DDPM update with classifier-free guidance and learned-range variance:
  * vqvae/utils/diffusion.py:317-386,472-485. */
 int dtts_p_sample_step(const dtts_pstep_params* p, void* stream);
+
+typedef struct {
+  const float* x; int ldx;       /* [M, Cp] fp32 stage input = ConvTranspose1d output (no activation); separators zero */
+  int M, Cp;                     /* rows at this stage's rate; padded channel count (16 or 32) */
+  const int* row_utt;            /* [M]: utterance of each row, -1 = separator (zero padding between utterances) */
+  const void* w_frag;            /* fp16 weights of the 18 convs as mma.sync B fragments, conv order
+                                    (k=3: c1_d1 c2 c1_d3 c2 c1_d5 c2), (k=7: ...), (k=11: ...); per conv [tap][Cp/8][Cp/16][32 lanes][4] */
+  const float* bias;             /* [18, Cp] fp32, same conv order */
+  float slope, slope_out;        /* leaky-ReLU slope inside the ResBlocks (0.1) / applied to the fp16 output */
+  void* out_f16; int ldo16;      /* lrelu_slope_out(mean of the three ResBlocks): operand of the next ConvTranspose1d / conv_post */
+  float* out_f32; int ldo32;     /* optional: the un-activated mean */
+} dtts_voc_mrf_params;
+/* Multi-receptive-field stage of the vocoder for the narrow stages, fused: xs = (RB_3(x) + RB_7(x) + RB_11(x)) / 3 with
+ * RB_k = 3 x [lrelu -> conv(k, d in 1,3,5) -> lrelu -> conv(k, 1) -> + x]  (vqvae/model_24k.py:276-283,
+ * vqvae/modules/modules.py:240-328).  One CTA keeps a 512-position tile (392 outputs + halo) in shared memory / registers
+ * through all 18 convs; HBM traffic is x in, out16 out. */
+int dtts_voc_mrf(const dtts_voc_mrf_params* p, void* stream);
+
+typedef struct {
+  const void* x; int ldx;        /* [M, 16] fp16 = lrelu_0.01(xs) of the last stage (12 channels padded to 16) */
+  int M, C;                      /* rows, real channels (<= 16) */
+  const int* row_utt;            /* [M] */
+  const float* w;                /* [7, C] fp32 conv_post weight (tap-major), no bias */
+  float* out; int ldo;           /* [M, ldo] waveform sample per row: tanh(conv) */
+} dtts_conv_post_params;
+/* conv_post + tanh: vqvae/model_24k.py:284-286 (Conv1d 12->1, k7, pad 3, no bias). */
+int dtts_conv_post(const dtts_conv_post_params* p, void* stream);
 
 /* elementwise / layout helpers (all on rows layout unless stated) */
 typedef struct {
