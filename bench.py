@@ -172,8 +172,16 @@ def gemm_roofline(model, lib, pk):
     tot_ms, tot_fl = sum(ms), sum(flops)
     ach = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
+    # DRAM bytes per launch of the same 62 launches from the committed ncu capture (never measured live under a profiler)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_C_gemm_traffic.json")))
+        if tj["launches"] == len(ms):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all 1x1/k3 conv GEMMs of one diffusion eval)",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
             "launches": len(ms), "avg_launch_us": 1000 * tot_ms / max(1, len(ms)),
             "flop_per_launch_avg": tot_fl / max(1, len(ms))}
 

@@ -39,3 +39,16 @@ tot = sum(v[1] for v in agg.values())
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1]:8.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:3d} avg {1000 * v[1] / v[0]:8.1f} us  {k}")
 print(f"decode step total {tot:.3f} ms (B={B}), {len(res)} launches")
+# CUDA-graph replay time of the decode step (what the generate loop actually pays per token)
+st = list(gpt._states.values())[0]
+if st.graph is not None:
+    for _ in range(3):
+        st.graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        st.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"decode step as one CUDA graph: {e0.elapsed_time(e1) / 50 * 1000:.1f} us per replay")

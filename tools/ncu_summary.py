@@ -53,6 +53,32 @@ def full(src, dst, comments):
                         for i in idx])
 
 
+def metrics(src, dst, comments):
+    """ncu --metrics a,b,c --csv log (one row per launch per metric) -> one row per launch."""
+    rows = [r for r in csv.reader(l for l in open(src, errors="replace") if l.startswith('"'))]
+    hdr = rows[0]
+    idc, kn, mn, mu, mv = (hdr.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value"))
+    per, names, order = {}, [], []
+    for r in rows[1:]:
+        if len(r) <= mv:
+            continue
+        key = r[idc]
+        if key not in per:
+            per[key] = {"kernel": r[kn].replace("void ", "").replace("<unnamed>::", "").split("(")[0]}
+            order.append(key)
+        col = f"{r[mn]} [{r[mu]}]"
+        if col not in names:
+            names.append(col)
+        per[key][col] = r[mv].replace(",", "")
+    with open(dst, "w") as f:
+        for c in comments:
+            f.write("# " + c + "\n")
+        w = csv.writer(f)
+        w.writerow(["launch", "kernel"] + names)
+        for i, key in enumerate(order):
+            w.writerow([i, per[key]["kernel"]] + [per[key].get(n, "") for n in names])
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
-    (launches if mode == "launches" else full)(src, dst, sys.argv[4:])
+    {"launches": launches, "full": full, "metrics": metrics}[mode](src, dst, sys.argv[4:])
