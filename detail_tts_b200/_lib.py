@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(HERE, "libdtts.so")
 _CT = {"int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64}
 
 # enums of dtts.h
-ACT_NONE, ACT_GELU_NEW, ACT_RELU, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_TANH = 0, 1, 2, 3, 4, 5, 6
+ACT_NONE, ACT_GELU_NEW, ACT_RELU, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_TANH, ACT_LOG_CLAMP = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_PAIR_TANH_SIGMOID, ACT_PAIR_GLU = 16, 17
 BIAS_NONE, BIAS_RELPOS_TABLE, BIAS_WINDOW_REL = 0, 1, 2
 

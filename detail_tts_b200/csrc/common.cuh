@@ -54,6 +54,7 @@ __device__ __forceinline__ float act_apply(int act, float x, float p) {
     }
     case DTTS_ACT_LRELU: return x > 0.0f ? x : x * p;
     case DTTS_ACT_TANH: return tanhf(x);
+    case DTTS_ACT_LOG_CLAMP: return logf(fmaxf(x, p));
     default: return x;
   }
 }

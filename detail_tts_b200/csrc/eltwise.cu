@@ -219,6 +219,45 @@ inline int grid_for(long total, int threads = 256) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// ---- prompt front-end: mel_spectrogram_torch (vqvae/utils/data_utils.py:105-155) ---------------------------------
+// STFT as a DFT GEMM on the 3xTF32 tensor-core path (fp32-class): this kernel builds the windowed frames
+// (reflect padding of (n_fft-hop)/2 samples at both ends, center=False) already split into tf32 hi/lo operands.
+__global__ void __launch_bounds__(256)
+stft_frames_kernel(const dtts_stft_frames_params p) {
+  const int b = blockIdx.y;
+  const int n = p.wav_len[b], nfr = p.utt_len[b];
+  const long row0 = p.utt_off[b];
+  const float* w = p.wav + (long)b * p.ldw;
+  const long total = (long)nfr * p.n_fft;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / p.n_fft), k = (int)(idx - (long)r * p.n_fft);
+    int i = r * p.hop + k - p.pad;
+    if (i < 0) i = -i;                       // reflect (no edge repeat), torch F.pad(mode="reflect")
+    if (i >= n) i = 2 * (n - 1) - i;
+    const float v = (i >= 0 && i < n) ? w[i] * __ldg(p.window + k) : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    p.out_hi[(row0 + r) * p.ld + k] = hi;
+    p.out_lo[(row0 + r) * p.ld + k] = v - hi;
+  }
+}
+
+// |X| = sqrt(re^2 + im^2 + 1e-6) from the DFT GEMM output [M, >= 2*n_bins] (re | im), split into tf32 hi/lo for the mel GEMM
+__global__ void __launch_bounds__(256)
+spec_mag_kernel(const dtts_spec_mag_params p) {
+  const long total = (long)p.M * p.ld;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / p.ld), f = (int)(idx - (long)m * p.ld);
+    float v = 0.f;
+    if (f < p.n_bins) {
+      const float re = p.spec[(long)m * p.lds + f], im = p.spec[(long)m * p.lds + p.n_bins + f];
+      v = sqrtf(re * re + im * im + p.eps);
+    }
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    p.out_hi[idx] = hi;
+    p.out_lo[idx] = v - hi;
+  }
+}
+
 }  // namespace
 
 extern "C" int dtts_p_sample_step(const dtts_pstep_params* p, void* stream) {
@@ -341,6 +380,28 @@ extern "C" int dtts_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return 0;
 }
 #define SZ(name) if (!strcmp(struct_name, #name)) return (int)sizeof(name)
+extern "C" int dtts_stft_frames(const dtts_stft_frames_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->wav && p->wav_len && p->utt_off && p->utt_len && p->window && p->out_hi && p->out_lo, "stft_frames: null argument");
+  DTTS_REQUIRE(p->n_fft > 0 && p->hop > 0 && p->pad >= 0 && p->ld >= p->n_fft, "stft_frames: bad shape");
+  if (p->n_utt <= 0 || p->max_frames <= 0) return 0;
+  long g = ((long)p->max_frames * p->n_fft + 255) / 256;
+  if (g > 2048) g = 2048;
+  stft_frames_kernel<<<dim3((unsigned)g, p->n_utt), 256, 0, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("stft_frames");
+  return 0;
+}
+
+extern "C" int dtts_spec_mag(const dtts_spec_mag_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->spec && p->out_hi && p->out_lo, "spec_mag: null argument");
+  DTTS_REQUIRE(p->n_bins > 0 && p->ld >= p->n_bins && p->lds >= 2 * p->n_bins, "spec_mag: bad shape");
+  if (p->M <= 0) return 0;
+  long g = ((long)p->M * p->ld + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  spec_mag_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("spec_mag");
+  return 0;
+}
+
 extern "C" int dtts_sizeof(const char* struct_name) {
   if (!struct_name) return -1;
   SZ(dtts_gemm_params); SZ(dtts_groupnorm_params); SZ(dtts_layernorm_params); SZ(dtts_attention_params);
@@ -348,6 +409,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_rows2bct_params); SZ(dtts_eltwise_params); SZ(dtts_embed_params); SZ(dtts_repeat_rows_params);
   SZ(dtts_mean_rows_params); SZ(dtts_tsemb_params); SZ(dtts_couple_params); SZ(dtts_zp_params);
   SZ(dtts_rowutt_params); SZ(dtts_copy_utts_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
-  SZ(dtts_voc_mrf_params); SZ(dtts_conv_post_params);
+  SZ(dtts_voc_mrf_params); SZ(dtts_conv_post_params); SZ(dtts_stft_frames_params); SZ(dtts_spec_mag_params);
   return -1;
 }

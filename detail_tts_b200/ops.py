@@ -7,7 +7,7 @@ synthesis path outside these wrappers except RNG draws and allocation.
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_NEW, ACT_LRELU, ACT_MISH, ACT_NONE, ACT_PAIR_GLU,  # noqa: F401
+from ._lib import (ACT_GELU_NEW, ACT_LOG_CLAMP, ACT_LRELU, ACT_MISH, ACT_NONE, ACT_PAIR_GLU,  # noqa: F401
                    ACT_PAIR_TANH_SIGMOID, ACT_RELU, ACT_SILU, ACT_TANH, BIAS_NONE,
                    BIAS_RELPOS_TABLE, BIAS_WINDOW_REL)
 
@@ -28,7 +28,7 @@ class PackedConv:
         self.w_lo = w_lo
 
 
-def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None, split_k=1, bias=True):
+def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None, split_k=1, bias=True, act_param=0.0):
     """fp32-class GEMM on tcgen05 (3xTF32).  split_k > 1: out32 is a partial buffer [split_k, M, N]
     (finish with splitk_reduce); otherwise the normal fused epilogue."""
     M = A_hi.shape[0]
@@ -41,7 +41,7 @@ def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None,
     _lib.lib().call("dtts_gemm_tf32x3", A=A_hi, A_lo=A_lo, W=pw.w, W_lo=pw.w_lo, M=M, N=pw.N, K=pw.K, lda=_ld(A_hi),
                     ldw=_ld(pw.w), taps=1, tap_shift0=0, tap_stride=1, bias=pw.bias if bias else None,
                     out_row_map=out_row_map, res=res, ldr=_ld(res) if res is not None else 0, out_f32=out32,
-                    ldo32=_ld(out32), act=act, alpha=1.0, split_k=1)
+                    ldo32=_ld(out32), act=act, act_param=act_param, alpha=1.0, split_k=1)
 
 
 def n_splits_for(K, split_k):

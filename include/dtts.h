@@ -30,6 +30,7 @@ enum {
   DTTS_ACT_MISH = 4,       /* vqvae/modules/modules.py:496-501 */
   DTTS_ACT_LRELU = 5,      /* vqvae/model_24k.py:275,284; modules.py:317,320 (slope in act_param) */
   DTTS_ACT_TANH = 6,       /* vqvae/model_24k.py:286 */
+  DTTS_ACT_LOG_CLAMP = 7,  /* log(max(x, act_param)): dynamic_range_compression_torch, vqvae/utils/data_utils.py:20-26 */
   /* pair activations: output column j is f(v[2j], v[2j+1]); N must be even, Nout = N/2.
      Weights are packed with the two halves of the reference's channel split interleaved. */
   DTTS_ACT_PAIR_TANH_SIGMOID = 16, /* fused_add_tanh_sigmoid_multiply, modules.py:15-22 */
@@ -206,6 +207,25 @@ typedef struct {
 } dtts_conv_post_params;
 /* conv_post + tanh: vqvae/model_24k.py:284-286 (Conv1d 12->1, k7, pad 3, no bias). */
 int dtts_conv_post(const dtts_conv_post_params* p, void* stream);
+
+typedef struct {
+  const float* wav; int ldw; const int* wav_len;   /* [n_utt, ldw] fp32 waveforms (24 kHz), valid samples per utterance */
+  int n_utt; const int* utt_off; const int* utt_len;   /* frame rows of utterance b: (wav_len + 2*pad - n_fft)/hop + 1 */
+  int max_frames;
+  int n_fft, hop, pad;          /* 1024, 256, (n_fft - hop)/2 = 384: reflect padding at both ends, center=False */
+  const float* window;          /* [n_fft] periodic Hann (torch.hann_window) */
+  float* out_hi; float* out_lo; int ld;   /* [M, n_fft] windowed frames split x = hi + lo (hi tf32-exact) */
+} dtts_stft_frames_params;
+/* Framing + windowing of mel_spectrogram_torch (vqvae/utils/data_utils.py:120-141: F.pad reflect + torch.stft framing).
+ * The DFT itself is dtts_gemm_tf32x3 against a [cos | -sin] basis (fp32-class). */
+int dtts_stft_frames(const dtts_stft_frames_params* p, void* stream);
+
+typedef struct {
+  const float* spec; int lds;   /* [M, >= 2*n_bins] DFT output: real parts then imaginary parts */
+  int M, n_bins; float eps;     /* 513 bins; sqrt(re^2 + im^2 + eps), eps = 1e-6 (data_utils.py:143) */
+  float* out_hi; float* out_lo; int ld;   /* [M, ld >= n_bins] magnitudes split hi/lo, zero beyond n_bins */
+} dtts_spec_mag_params;
+int dtts_spec_mag(const dtts_spec_mag_params* p, void* stream);
 
 /* elementwise / layout helpers (all on rows layout unless stated) */
 typedef struct {

@@ -207,3 +207,48 @@ def test_scatter_gather_gloo_world2():
     for p in ps:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_mrf_fragment_packing_roundtrip():
+    """pack_mrf_fragments lays conv weights out as mma.sync m16n8k16 B fragments: lane g*4+tig of (tap, n-tile, k-step) holds
+    W[tap][n = nt*8+g][k = ks*16 + 2*tig + {0,1,8,9}] (dtts_voc_mrf, include/dtts.h).  Rebuild the weights from the fragments."""
+    import torch
+    from detail_tts_b200 import pack
+    g = torch.Generator().manual_seed(0)
+    for C, cp in ((12, 16), (25, 32)):
+        convs = []
+        for k in (3, 3, 7, 11):
+            convs.append((torch.randn(C, C, k, generator=g), torch.randn(C, generator=g)))
+        wf, bias = pack.pack_mrf_fragments(convs, cp, "cpu")
+        assert wf.dtype == torch.float16 and bias.shape == (len(convs), cp)
+        NT, KS = cp // 8, cp // 16
+        off = 0
+        for ci, (w, b) in enumerate(convs):
+            k = w.shape[2]
+            n = k * NT * KS * 32 * 4
+            f = wf[off:off + n].view(k, NT, KS, 32, 4).float()
+            off += n
+            W = torch.zeros(k, cp, cp)
+            for lane in range(32):
+                gq, tig = lane >> 2, lane & 3
+                for nt in range(NT):
+                    for ks in range(KS):
+                        for e, dk in enumerate((0, 1, 8, 9)):
+                            W[:, nt * 8 + gq, ks * 16 + 2 * tig + dk] = f[:, nt, ks, lane, e]
+            ref = torch.zeros(k, cp, cp)
+            ref[:, :C, :C] = w.permute(2, 0, 1).half().float()
+            assert torch.equal(W, ref)
+            assert torch.equal(bias[ci, :C], b) and float(bias[ci, C:].abs().sum()) == 0
+        assert off == wf.numel()
+
+
+def test_slaney_filterbank_matches_oracle():
+    """The product's mel filterbank (detail_tts_b200/frontend.py, numpy) against the oracle's independent restatement."""
+    import torch
+    import oracle.frontend as ofe
+    from detail_tts_b200.frontend import slaney_mel_filterbank
+    a = torch.from_numpy(slaney_mel_filterbank(24000, 1024, 128, 0.0, None))
+    b = ofe.mel_basis(24000, 1024, 128, 0.0, None)
+    assert a.shape == b.shape == (128, 513)
+    assert float((a - b).abs().max()) < 1e-7
+    assert float(a.sum(1).min()) > 0        # every filter has support at n_fft = 1024

@@ -124,3 +124,16 @@ def test_tokenizer_known_answer():
         txt = txt.replace(k, v)
     ids = tok.encode(txt.replace(" ", "[SPACE]")).ids
     assert ids == kat["ids"][:-1]
+
+
+def test_frontend_oracle_matches_reference_melspec():
+    """oracle/frontend.py against the reference's own mel_spectrogram_torch (tests/golden/melspec.pt, written by
+    tests/golden/make_melspec.py from /root/reference/vqvae/utils/data_utils.py:105-155)."""
+    import os
+    import torch
+    import oracle.frontend as ofe
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "melspec.pt"))
+    for name, item in fx.items():
+        mel = ofe.mel_spectrogram(item["wav"])
+        assert mel.shape == item["mel"].shape, name
+        assert float((mel - item["mel"]).abs().max()) < 2e-4, name

@@ -257,3 +257,28 @@ def test_batch_equals_per_utterance(model):
         assert torch.equal(trb["codes"][b].cpu(), tr1["codes"][0].cpu())
         n = int(wl_1[0])
         assert rms(wav_b[b, :, :n], wav_1[0, :, :n]) < 2e-4
+
+
+def test_frontend_melspec_matches_reference():
+    """Prompt front-end: GPU DFT-GEMM mel spectrogram against the reference's mel_spectrogram_torch
+    (golden from /root/reference), then a ragged batch against per-utterance calls."""
+    import os
+    from detail_tts_b200 import frontend
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "melspec.pt"))
+    for name, item in fx.items():
+        mel = frontend.mel_spectrogram_torch(item["wav"].to(DEV), 1024, 128, 24000, 256, 1024, 0.0, None, device=DEV)
+        assert mel.shape == item["mel"].shape, name
+        d = (mel.cpu() - item["mel"]).abs()
+        print(name, "max abs", float(d.max()), "rms", float(d.pow(2).mean().sqrt()))
+        assert float(d.max()) < 2e-3 and float(d.pow(2).mean().sqrt()) < 1e-4, name
+    fe = frontend.MelFrontEnd(1024, 128, 24000, 256, 1024, 0.0, None, DEV)
+    wav = fx["synthetic"]["wav"]
+    lens = [12000, 5000, 7777]
+    batch = wav.clone()
+    for b, n in enumerate(lens):
+        batch[b, n:] = 0
+    mel_b, frames = fe(batch.to(DEV), lens)
+    for b, n in enumerate(lens):
+        one, fr1 = fe(wav[b:b + 1, :n].to(DEV))
+        assert frames[b] == fr1[0] == n // 256
+        assert torch.equal(mel_b[b, :, :frames[b]], one[0])
