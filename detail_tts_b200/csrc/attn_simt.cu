@@ -286,6 +286,8 @@ constexpr int DEC_WARPS = 4;
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attention_decode_kernel(const dtts_attention_params p) {
   extern __shared__ float sm[];
+  pdl_launch();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x * DEC_WARPS + warp, b = blockIdx.y;
   if (h >= p.n_heads || p.q_len[b] <= 0) return;
@@ -389,7 +391,7 @@ extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) 
       dec_attr = true;
     }
     dim3 grid(ceil_div(p->n_heads, DEC_WARPS), p->n_utt);
-    attention_decode_kernel<<<grid, DEC_WARPS * 32, (size_t)DEC_WARPS * p->max_k_len * sizeof(float), (cudaStream_t)stream>>>(*p);
+    launch_maybe_pdl(attention_decode_kernel, grid, dim3(DEC_WARPS * 32), (size_t)DEC_WARPS * p->max_k_len * sizeof(float), (cudaStream_t)stream, *p);
     DTTS_CHECK_LAUNCH("attention_decode");
     return 0;
   }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 
 #include "../../include/dtts.h"
 
@@ -34,6 +35,31 @@ extern int g_dtts_launches;
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL) for the latency-bound GPT decode step: the ~94 small kernels of a
+// step are launched with cudaLaunchAttributeProgrammaticStreamSerialization while dtts_set_pdl(1) is in
+// effect, so kernel N+1 is scheduled (and runs its prologue) while kernel N drains.  Every such kernel
+// calls pdl_launch() first and pdl_wait() before it touches memory written by its predecessor; both are
+// no-ops for a normal launch.
+// ---------------------------------------------------------------------------------------------
+extern int g_dtts_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dtts_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // device: activations

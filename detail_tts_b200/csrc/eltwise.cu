@@ -5,6 +5,7 @@
 
 thread_local char g_dtts_err[512] = {0};
 int g_dtts_launches = 0;
+int g_dtts_pdl = 0;
 
 namespace {
 
@@ -369,6 +370,7 @@ extern "C" int dtts_fill_row_utt(const dtts_rowutt_params* p, void* stream) {
 extern "C" int dtts_abi_version(void) { return DTTS_ABI_VERSION; }
 extern "C" const char* dtts_last_error(void) { return g_dtts_err; }
 extern "C" int dtts_kernel_launches(void) { return g_dtts_launches; }
+extern "C" int dtts_set_pdl(int on) { const int old = g_dtts_pdl; g_dtts_pdl = on ? 1 : 0; return old; }
 extern "C" int dtts_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) DTTS_FAIL(-6, "device_info: no CUDA device");

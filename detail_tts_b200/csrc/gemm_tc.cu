@@ -33,9 +33,12 @@ constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
 // TF32 = true: 3xTF32 fp32-class GEMM.  Operands are fp32 split on the host side of the ABI into a
 // tf32-exact high part and a low part (x = hi + lo); a stage holds {A_hi, A_lo, W_hi, W_lo} tiles (32 fp32 =
 // 128 B rows, same swizzle span) and the MMA warp issues hi*hi + lo*hi + hi*lo (kind::tf32, K=8 per MMA).
-template <int BN, bool TF32 = false>
+// CTAS = 2: cta_group::2 -- a pair of CTAs (one cluster, two SMs of a TPC) computes a 256 x BN tile; each CTA stages its own
+// 128 rows of A and HALF of the B tile, the leader's tcgen05.mma reads both halves, each CTA's TMEM receives its 128 rows
+// of the accumulator.  Shared-memory operand traffic per SM per MMA drops from 4 + BN/32 KB to 4 + BN/64 KB.
+template <int BN, bool TF32 = false, int CTAS = 1>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;   // BN rows x 128 B, for fp16 (64 el) and tf32 (32 el) alike
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // rows of B staged by one CTA x 128 B, for fp16 (64 el) and tf32 (32 el) alike
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -45,13 +48,19 @@ struct Cfg {
 };
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int BN, bool TF32>
+template <int BN, bool TF32, int CTAS = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride,
                const int kb_per_split, const long split_stride, const int debug) {
-  using C = Cfg<BN, TF32>;
+  using C = Cfg<BN, TF32, CTAS>;
+  static_assert(CTAS == 1 || !TF32, "the CTA-pair variant is fp16 only");
+  uint32_t cta_rank = 0;
+  if (CTAS == 2) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int work_id = CTAS == 2 ? blockIdx.x >> 1 : blockIdx.x;        // tile stream of this CTA (pair)
+  const int work_stride = CTAS == 2 ? gridDim.x >> 1 : gridDim.x;
   constexpr int BKE = TF32 ? 32 : 64;   // elements per 128-byte K block
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries of the SHARED address space
@@ -66,7 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (epi.M + BM - 1) / BM;
+  const int m_tiles = (epi.M + CTAS * BM - 1) / (CTAS * BM);
   const int n_tiles = (epi.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   // split-K: blockIdx.y owns K blocks [kb0, kb0 + k_blocks) and writes a raw partial tile set at
@@ -79,18 +88,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CTAS * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (TF32) {   // GPT decode step: programmatic dependent launch (no-op otherwise); the prologue above overlapped the predecessor
+    pdl_launch();
+    pdl_wait();
+  }
 
   if (warp == 0) {
     // ================================ TMA producer =================================
@@ -102,15 +121,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
       }
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int tile = work_id; tile < num_tiles; tile += work_stride) {
+        const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
+        const int n0 = (tile % n_tiles) * BN + (int)cta_rank * (BN / CTAS);
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / k_blocks;
           const int kb = it - tap * k_blocks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
+          if (CTAS == 2) {
+            // both CTAs' loads complete on the LEADER's barrier (its own arrive.expect_tx covers the pair's bytes)
+            if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, &full[stage], (kb0 + kb) * BKE, m0 + tap_shift0 + tap * tap_stride);
+            tma_load_2d_pair(sb, &tmW, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full[stage], (kb0 + kb) * BKE, m0 + tap_shift0 + tap * tap_stride);
           tma_load_2d(sb, &tmW, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
@@ -124,11 +151,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN) | (TF32 ? ((2u << 7) | (2u << 10)) : 0u);   // a/b format: F16 = 0, TF32 = 2
+    if (lane == 0 && leader) {   // CTA pair: the leader issues for both CTAs (cta_group::2)
+      const uint32_t idesc = make_idesc(CTAS * BM, BN) | (TF32 ? ((2u << 7) | (2u << 10)) : 0u);   // a/b format: F16 = 0, TF32 = 2
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = work_id; tile < num_tiles; tile += work_stride) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -142,7 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {   // 4 x (K=16 fp16 = 32 B)
               const uint64_t da = make_desc(sa + k * 32);
               const uint64_t db = make_desc(sb + k * 32);
-              umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              if (CTAS == 2) umma_f16_pair(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           } else {
             const uint32_t sa2 = sb + C::B_BYTES, sb2 = sa2 + A_BYTES;
@@ -155,10 +183,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (CTAS == 2) tc_commit_pair(&empty[stage]);   // multicast: frees the slot in both CTAs
+          else tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
+        if (CTAS == 2) tc_commit_pair(&tfull[acc]);
+        else tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -180,8 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // validity comes from a per-tile bitmask loaded while the MMAs still run, all residual loads are issued first.
     const bool lean = fast && epi.act == DTTS_ACT_NONE && (epi.act16 == DTTS_ACT_NONE || epi.act16 == DTTS_ACT_LRELU) && !epi.bias_utt;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM;
+    for (int tile = work_id; tile < num_tiles; tile += work_stride) {
+      const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
       const int n0 = (tile % n_tiles) * BN;
       const int mrow = m0 + q * 32 + (lane >> 3);   // + it*4
       uint32_t vmask = 0;
@@ -270,17 +300,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_leader(&tempty[acc]);   // the leader's issuer waits for both CTAs' epilogues
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
@@ -322,6 +357,42 @@ std::mutex g_maps_mu;
 int g_sm_count = 0;
 int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
+// CTA-pair (cta_group::2) launch: fp16 only, 256 x BN tiles, one 2-CTA cluster per tile stream
+template <int BN>
+int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
+  using C = Cfg<BN, false, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc pair<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap ma, mw;
+  int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma, 2);
+  if (rc) return rc;
+  rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN / 2, &mw, 2);
+  if (rc) return rc;
+  const int pairs = ceil_div(p->M, 2 * BM) * ceil_div(p->N, BN);
+  const int kb_all = ceil_div(p->K, 64);
+  EpiParams e = make_epi(p);
+  int grid = 2 * pairs < g_sm_count ? 2 * pairs : (g_sm_count & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2>, ma, mw, ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+                                      kb_all, (long)0, g_debug);
+  if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc pair launch failed: %s", cudaGetErrorString(le));
+  DTTS_CHECK_LAUNCH("gemm_tc_pair");
+  return 0;
+}
+
 template <int BN, bool TF32>
 int launch(const dtts_gemm_params* p, cudaStream_t st) {
   using C = Cfg<BN, TF32>;
@@ -356,8 +427,14 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
     e.act = DTTS_ACT_NONE; e.act16 = DTTS_ACT_NONE; e.alpha = 1.0f; e.accumulate = 0; e.row_utt = nullptr;
   }
   dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
-  gemm_tc_kernel<BN, TF32><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
-                                                                      kb_per, (long)p->split_stride, g_debug);
+  if (TF32) {
+    cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, e, p->K, p->taps,
+                                      p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
+    if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc launch failed: %s", cudaGetErrorString(le));
+  } else {
+    gemm_tc_kernel<BN, TF32><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+                                                                        kb_per, (long)p->split_stride, g_debug);
+  }
   DTTS_CHECK_LAUNCH("gemm_tc");
   return 0;
 }
@@ -427,6 +504,11 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   const int N = p->N;
   static int bn256 = -1;   // 256-wide tiles (less shared-memory read traffic per MMA): +5 % on the diffusion shapes
   if (bn256 < 0) { const char* e = getenv("DTTS_GEMM_BN256"); bn256 = e ? atoi(e) : 1; }
+  // cta_group::2 tiles (256 x 256 per CTA pair) for the long-K GEMMs (k3 convs, K = 1536): +8..12 % measured; the K = 768
+  // 1x1 convs are epilogue / HBM-bound and lose 3-5 % to the pair synchronisation, so they stay on single-CTA tiles
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("DTTS_GEMM_PAIR"); pair = e ? atoi(e) : 1; }
+  if (pair && N % 256 == 0 && p->M >= 4096 && (long)p->K * p->taps >= 1536) return launch_pair<256>(p, st);
   if (bn256 && N % 256 == 0) return launch<256, false>(p, st);
   if (N % 192 == 0) return launch<192, false>(p, st);
   if (N > 64) return launch<128, false>(p, st);

@@ -34,6 +34,8 @@ template <bool LN>
 __global__ void __launch_bounds__(RED_THREADS)
 reduce_kernel(const dtts_reduce_params p) {
   __shared__ float red[40];
+  pdl_launch();
+  pdl_wait();
   const int m = blockIdx.x;
   const long orow = p.out_row_map ? (long)p.out_row_map[m] : (long)m;
   float vals[RED_MAXE];
@@ -108,9 +110,9 @@ extern "C" int dtts_splitk_reduce(const dtts_reduce_params* p, void* stream) {
   if (p->M <= 0) return 0;
   if (p->ln_gamma) {
     DTTS_REQUIRE(p->ln_beta && p->N <= RED_THREADS * RED_MAXE, "splitk_reduce: LayerNorm path needs N <= 1024");
-    reduce_kernel<true><<<p->M, RED_THREADS, 0, (cudaStream_t)stream>>>(*p);
+    launch_maybe_pdl(reduce_kernel<true>, dim3(p->M), dim3(RED_THREADS), 0, (cudaStream_t)stream, *p);
   } else {
-    reduce_kernel<false><<<p->M, RED_THREADS, 0, (cudaStream_t)stream>>>(*p);
+    launch_maybe_pdl(reduce_kernel<false>, dim3(p->M), dim3(RED_THREADS), 0, (cudaStream_t)stream, *p);
   }
   DTTS_CHECK_LAUNCH("splitk_reduce");
   return 0;

@@ -296,8 +296,8 @@ groupnorm_reg_kernel(const T* __restrict__ x, int ldx, int cpg, const int* __res
 constexpr int GNT_BOX_ROWS = 32, GNT_STAGES = 2, GNT_ROW_BYTES = 192, GNT_MAX_SMEM = 224 * 1024;
 
 template <typename T>
-__global__ void __launch_bounds__(GNR_THREADS, 2)
-groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, int n_gx, int n_utt, int stage_rows,
+__global__ void __launch_bounds__(GNR_THREADS, 3)
+groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, int n_gx, int n_utt, int stage_rows, int n_stages,
                      const int* __restrict__ utt_off, const int* __restrict__ utt_len, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film_scale, const float* __restrict__ film_shift,
                      int ld_film, const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
@@ -317,7 +317,7 @@ groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, i
   const int g = (col * 4) / cpg;
   const int n_items = n_utt * n_gx;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GNT_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -333,15 +333,15 @@ groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, i
   };
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm) : "memory");
-    for (int s = 0; s < GNT_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       const int item = blockIdx.x + s * gridDim.x;
       if (item < n_items) issue(item, s);
     }
   }
   int it = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-    const int stage = it % GNT_STAGES;
-    const uint32_t phase = (it / GNT_STAGES) & 1;
+    const int stage = it % n_stages;
+    const uint32_t phase = (it / n_stages) & 1;
     const int b = item / n_gx, gx = item - b * n_gx;
     const int T_ = utt_len[b];
     const long row0 = utt_off[b];
@@ -411,10 +411,139 @@ groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tm, int cpg, int gpc, i
     }
     __syncthreads();                                         // every thread is done with this stage's buffer
     if (threadIdx.x == 0) {
-      const int nxt = item + GNT_STAGES * gridDim.x;
+      const int nxt = item + n_stages * gridDim.x;
       if (nxt < n_items) issue(nxt, stage);
     }
   }
+}
+
+// Cluster variant (default for the diffusion hot loop).  The strip kernels above read 192-byte segments at a
+// 1.5-3 KB stride, which caps them near 4 TB/s (DRAM page locality), whatever the staging.  Here a thread-block
+// cluster owns one utterance and every CTA of it streams a CONTIGUOUS block of whole rows (all channels) with 1-D
+// bulk copies (cp.async.bulk, mbarrier completion) into shared memory; the per-group partial sums of the CTAs are
+// combined through distributed shared memory (two exchanges: mean, then centred sum of squares = exact two-pass
+// statistics, fixed summation order), and the normalised fp16 operand is written back as whole contiguous rows.
+constexpr int GNC_THREADS = 384, GNC_MAX_GROUPS = 64, GNC_MAX_CLUSTER = 8, GNC_CHUNK = 32 * 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(GNC_THREADS, 2)
+groupnorm_cluster_kernel(const T* __restrict__ x, int C, int cpg, int groups, const int* __restrict__ utt_off,
+                         const int* __restrict__ utt_len, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ film_scale, const float* __restrict__ film_shift, int ld_film,
+                         const int* __restrict__ film_idx, int act, float eps, float* __restrict__ out32, int ldo32,
+                         __half* __restrict__ out16, int ldo16) {
+  using namespace dtts_tc;
+  typedef typename GnVec<T>::Raw Raw;
+  extern __shared__ uint8_t gnc_smem_raw[];
+  uint8_t* smem = gnc_smem_raw + ((128u - (smem_u32(gnc_smem_raw) & 127u)) & 127u);
+  __shared__ float part[GNC_THREADS];                 // per-thread partials of the current pass
+  __shared__ float gsum[2][GNC_MAX_GROUPS];           // this CTA's per-group partial sums: [0] sum, [1] centred sum of squares
+  __shared__ float gstat[2][GNC_MAX_GROUPS];          // cluster-wide mean / rstd
+  __shared__ __align__(8) uint64_t bar;
+  uint32_t cs, rank;
+  asm("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x / cs;
+  const int T_ = utt_len[b];
+  const long row0 = utt_off[b];
+  const int rows_per = (T_ + (int)cs - 1) / (int)cs;
+  const int r0 = min(T_, (int)rank * rows_per), r1 = min(T_, r0 + rows_per), n = r1 - r0;
+  const int C4 = C >> 2;                               // 4-channel vectors per row; the launcher guarantees 384 % C4 == 0,
+  const int rs = GNC_THREADS / C4;                     // so a thread's channel column (and group) is fixed
+  const int col = threadIdx.x % C4;
+  const int vpg = cpg >> 2;                            // vectors per group per row
+  const int g = col / vpg;
+  const long bytes = (long)n * C * sizeof(T);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bar, (uint32_t)bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(x + (row0 + r0) * C);
+    for (long o = 0; o < bytes; o += GNC_CHUNK) {
+      const uint32_t sz = (uint32_t)(bytes - o < GNC_CHUNK ? bytes - o : GNC_CHUNK);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem + o)), "l"(src + o), "r"(sz), "r"(smem_u32(&bar)) : "memory");
+    }
+  }
+  __syncthreads();
+  const int nvec = n * C4;
+  const Raw* buf = reinterpret_cast<const Raw*>(smem);
+  const float inv_n = 1.0f / ((float)T_ * cpg);
+  mbar_wait(&bar, 0);
+  // ---- pass 1 / pass 2: per-group partial sums in a fixed order: thread -> shared -> one thread per group -> cluster (DSMEM)
+  for (int pass = 0; pass < 2; ++pass) {
+    const float mean = pass ? gstat[0][g] : 0.f;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < nvec; e += GNC_THREADS) {
+      float f[4];
+      GnVec<T>::unpack(buf[e], f);
+      if (pass == 0) s += (f[0] + f[1]) + (f[2] + f[3]);
+      else {
+        const float a0 = f[0] - mean, a1 = f[1] - mean, a2 = f[2] - mean, a3 = f[3] - mean;
+        s += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      float t = 0.f;
+      for (int rr = 0; rr < rs; ++rr)
+        for (int j = 0; j < vpg; ++j) t += part[rr * C4 + threadIdx.x * vpg + j];
+      gsum[pass][threadIdx.x] = t;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < groups) {
+      float t = 0.f;
+      const uint32_t local = smem_u32(&gsum[pass][threadIdx.x]);
+      for (uint32_t c = 0; c < cs; ++c) {
+        uint32_t remote;
+        float v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+        t += v;
+      }
+      gstat[pass][threadIdx.x] = pass ? rsqrtf(t * inv_n + eps) : t * inv_n;
+    }
+    __syncthreads();
+  }
+  // ---- pass 3: normalise + affine (+FiLM) (+SiLU), whole contiguous rows out
+  {
+    const int c = col * 4;
+    const float mean = gstat[0][g], rstd = gstat[1][g];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float A_[4] = {rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w};
+    float B_[4] = {be.x - mean * A_[0], be.y - mean * A_[1], be.z - mean * A_[2], be.w - mean * A_[3]};
+    if (film_scale) {   // (x*A+B)*(1+fs)+fb = x*A(1+fs) + B(1+fs)+fb
+      const long fr = film_idx ? film_idx[b] : b;
+      const float4 fs = *reinterpret_cast<const float4*>(film_scale + fr * ld_film + c);
+      const float4 fb = *reinterpret_cast<const float4*>(film_shift + fr * ld_film + c);
+      const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { A_[q] *= f1[q]; B_[q] = B_[q] * f1[q] + f0[q]; }
+    }
+    float* o32 = out32 ? out32 + (row0 + r0 + threadIdx.x / C4) * ldo32 + c : nullptr;
+    __half* o16 = out16 ? out16 + (row0 + r0 + threadIdx.x / C4) * ldo16 + c : nullptr;
+    const long s32 = (long)rs * ldo32, s16 = (long)rs * ldo16;
+    for (int e = threadIdx.x; e < nvec; e += GNC_THREADS) {
+      float y[4];
+      GnVec<T>::unpack(buf[e], y);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[q] = fmaf(y[q], A_[q], B_[q]);
+      if (act == DTTS_ACT_SILU) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = silu_fast(y[q]);
+      }
+      if (o32) { *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]); o32 += s32; }
+      if (o16) {
+        __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+        *reinterpret_cast<uint2*>(o16) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        o16 += s16;
+      }
+    }
+  }
+  // no CTA may exit while a peer can still read its gsum through DSMEM
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 constexpr int LN_MAXE = 32;  // C <= 1024
@@ -479,15 +608,63 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
   }
   cudaStream_t st0 = (cudaStream_t)stream;
   {
+    // cluster path (see groupnorm_cluster_kernel): contiguous rows, C/4 vector columns dividing the CTA size
+    static int cl_on = -1;
+    if (cl_on < 0) {
+      const char* e = getenv("DTTS_GN_CLUSTER");
+      cl_on = e ? atoi(e) : 0;   // measured on B200 (B=128, F=280): 106 / 111 us vs 82 / 78 us for the register path
+      cudaError_t e1 = cudaFuncSetAttribute(groupnorm_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      cudaError_t e2 = cudaFuncSetAttribute(groupnorm_cluster_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); cl_on = 0; }
+    }
+    const int es = p->x_is_f16 ? 2 : 4;
+    const int C4 = p->C / 4;
+    const int cs = GNC_MAX_CLUSTER;
+    const int rows_per = (p->max_len + cs - 1) / cs;
+    const size_t smem = 128 + (size_t)rows_per * p->C * es;
+    const bool aligned = ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->x)) & 15) == 0 &&
+                         (!p->film_scale || (((((uintptr_t)p->film_scale) | ((uintptr_t)p->film_shift)) & 15) == 0 && p->ld_film % 4 == 0)) &&
+                         (!p->out_f32 || ((((uintptr_t)p->out_f32) & 15) == 0 && p->ldo32 % 4 == 0)) &&
+                         (!p->out_f16 || ((((uintptr_t)p->out_f16) & 7) == 0 && p->ldo16 % 4 == 0));
+    if (cl_on && p->max_len > 0 && p->ldx == p->C && p->C % 4 == 0 && C4 <= GNC_THREADS && GNC_THREADS % C4 == 0 && cpg % 4 == 0 &&
+        p->groups <= GNC_MAX_GROUPS && (p->C * es) % 16 == 0 && aligned && smem <= 112 * 1024) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(cs * p->n_utt));
+      cfg.blockDim = dim3(GNC_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st0;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le;
+      if (p->x_is_f16)
+        le = cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel<__half>, (const __half*)p->x, p->C, cpg, p->groups, p->utt_off, p->utt_len,
+                                p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32,
+                                p->ldo32, (__half*)p->out_f16, p->ldo16);
+      else
+        le = cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel<float>, (const float*)p->x, p->C, cpg, p->groups, p->utt_off, p->utt_len,
+                                p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32,
+                                p->ldo32, (__half*)p->out_f16, p->ldo16);
+      if (le != cudaSuccess) DTTS_FAIL(-3, "groupnorm_cluster launch failed: %s", cudaGetErrorString(le));
+      DTTS_CHECK_LAUNCH("groupnorm_cluster");
+      return 0;
+    }
+  }
+  {
     // TMA-staged persistent path (see groupnorm_tma_kernel): strips of exactly 192 bytes per row
     const int es = p->x_is_f16 ? 2 : 4;
     const int gpc = cpg * es <= GNT_ROW_BYTES ? GNT_ROW_BYTES / (cpg * es) : 0;
     const int stage_rows = (p->max_len + GNT_BOX_ROWS - 1) / GNT_BOX_ROWS * GNT_BOX_ROWS;
-    const size_t smem = 128 + 128 + (size_t)GNT_STAGES * stage_rows * GNT_ROW_BYTES;
-    static int tma_on = -1, sms = 0;
+    static int tma_on = -1, sms = 0, n_stages = 1;
+    const size_t smem = 128 + 128 + (size_t)n_stages * stage_rows * GNT_ROW_BYTES;
     if (tma_on < 0) {
       const char* e = getenv("DTTS_GN_TMA");
       tma_on = e ? atoi(e) : 0;   // measured on B200 (B=128, F=280): 90.7 / 81.3 us vs 84.7 / 80.2 us for the register path
+      const char* e3 = getenv("DTTS_GN_TMA_STAGES");
+      n_stages = e3 ? atoi(e3) : 1;
+      if (n_stages < 1 || n_stages > GNT_STAGES) n_stages = 1;
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -508,14 +685,15 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
       if (rc) return rc;
       const int n_gx = p->groups / gpc;
       const long items = (long)p->n_utt * n_gx;
-      const int per_sm = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
+      int per_sm = (int)((227 * 1024) / (smem + 1024));
+      per_sm = per_sm > 3 ? 3 : per_sm < 1 ? 1 : per_sm;
       const int grid = items < (long)per_sm * sms ? (int)items : per_sm * sms;
       if (p->x_is_f16)
-        groupnorm_tma_kernel<__half><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, p->utt_off, p->utt_len,
+        groupnorm_tma_kernel<__half><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, n_stages, p->utt_off, p->utt_len,
             p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32,
             (__half*)p->out_f16, p->ldo16);
       else
-        groupnorm_tma_kernel<float><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, p->utt_off, p->utt_len,
+        groupnorm_tma_kernel<float><<<grid, GNR_THREADS, smem, st0>>>(tm, cpg, gpc, n_gx, p->n_utt, stage_rows, n_stages, p->utt_off, p->utt_len,
             p->gamma, p->beta, p->film_scale, p->film_shift, p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32,
             (__half*)p->out_f16, p->ldo16);
       DTTS_CHECK_LAUNCH("groupnorm_tma");

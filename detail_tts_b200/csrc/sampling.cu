@@ -22,6 +22,8 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 
 __global__ void __launch_bounds__(PL_THREADS)
 process_logits_kernel(const dtts_logits_params p) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sh[];          // [vocab] scores
   __shared__ uint32_t bitmap[512];       // vocab <= 16384
   __shared__ uint32_t hist[256];
@@ -203,7 +205,7 @@ extern "C" int dtts_process_logits(const dtts_logits_params* p, void* stream) {
   DTTS_REQUIRE(p->do_sample ? (p->probs != nullptr) : (p->argmax != nullptr), "process_logits: missing output");
   DTTS_REQUIRE(!p->do_sample || (p->temperature > 0.f && p->top_k > 0 && p->top_k <= 512), "process_logits: bad sampling params");
   if (p->n_rows <= 0) return 0;
-  process_logits_kernel<<<p->n_rows, PL_THREADS, p->vocab * sizeof(float), (cudaStream_t)stream>>>(*p);
+  launch_maybe_pdl(process_logits_kernel, dim3(p->n_rows), dim3(PL_THREADS), p->vocab * sizeof(float), (cudaStream_t)stream, *p);
   DTTS_CHECK_LAUNCH("process_logits");
   return 0;
 }

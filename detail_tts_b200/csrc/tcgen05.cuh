@@ -98,6 +98,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 
+// ---- cta_group::2 (CTA pair) variants.  Shared::cluster addresses of the two CTAs of a pair differ in bit 24; clearing
+// it addresses the leader (rank 0) -- the same convention as CUTLASS' Sm100MmaPeerBitMask.
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair when the prior MMAs retire
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the LEADER's copy of a barrier (local for the leader, remote for its peer)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+}
+
 // tensor-map cache (host): 2D map over a row-major [rows, cols] matrix (ld elements), box [box_rows, 128 bytes],
 // 128B swizzle; esize 2 = fp16, 4 = fp32.  Defined in gemm_tc.cu.
 int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int esize = 2);

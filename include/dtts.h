@@ -315,6 +315,10 @@ int dtts_abi_version(void);
 const char* dtts_last_error(void);
 int dtts_sizeof(const char* struct_name);   /* sizeof(<struct>) for the binding's layout self-check */
 int dtts_kernel_launches(void);             /* kernels launched by this library since load (bench gpu_launches) */
+/* While on, the kernels of the GPT decode step (dtts_gemm_tf32x3, dtts_splitk_reduce, the KV-cache path of
+ * dtts_attention_f32, dtts_process_logits) are launched with programmatic stream serialization (PDL): each is scheduled
+ * while its predecessor drains and waits (griddepcontrol.wait) before touching memory.  Returns the previous setting. */
+int dtts_set_pdl(int on);
 int dtts_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 #ifdef __cplusplus

@@ -70,7 +70,9 @@ CASES = [
     (700, 104, 104, 11, -25, 5),
     (64, 1536, 768, 1, 0, 1),
     (2, 768, 3072, 1, 0, 1),
-    (4096, 768, 1536, 1, 0, 1),
+    (4096, 768, 1536, 1, 0, 1),      # cta_group::2 path (N % 256 == 0, M >= 4096, K*taps >= 1536)
+    (4500, 256, 768, 3, -1, 1),      # ... with conv taps and a ragged last 256-row pair tile
+    (4230, 512, 1536, 1, 0, 1),      # ... last pair tile: the second CTA entirely out of range
 ]
 
 

@@ -49,4 +49,6 @@ for name, N, K, taps, res, o32, o16 in SHAPES:
     ms = e0.elapsed_time(e1) / n
     fl = 2.0 * M * N * K * taps
     byts = M * K * 2 + (M * N * 4 if res else 0) + (M * N * 4 if o32 else 0) + (M * N * 2 if o16 else 0)
-    print(f"{name:24s} {ms*1000:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  min-HBM {byts/ms/1e6:7.1f} GB/s")
+    O = sets[0][4] if o32 else sets[0][5]
+    chk = f"checksum {float(O.double().abs().sum()):.6e} sample {float(O[min(12345, M - 1), 7]):+.6f} {float(O[M - 1, N - 1]):+.6f}"
+    print(f"{name:24s} {ms*1000:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  min-HBM {byts/ms/1e6:7.1f} GB/s  {chk}")
