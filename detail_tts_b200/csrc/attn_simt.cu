@@ -305,7 +305,8 @@ attention_decode_kernel(const dtts_attention_params p) {
     q4[i].x *= p.scale; q4[i].y *= p.scale; q4[i].z *= p.scale; q4[i].w *= p.scale;
   }
   float lmax = -INFINITY;
-  for (int j0 = 0; j0 < nk; j0 += 8) {
+#pragma unroll 4
+  for (int j0 = 0; j0 < nk; j0 += 8) {   // unrolled: the (latency-bound) key loads of 4 iterations are in flight together
     const int j = j0 + kl;
     float s = 0.f;
     if (j < nk) {
@@ -336,6 +337,7 @@ attention_decode_kernel(const dtts_attention_params p) {
   const int g2 = lane / 12, d4 = lane % 12;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (g2 < 2) {
+#pragma unroll 8
     for (int j = g2; j < nk; j += 2) {
       const float pj = sc[j];
       const float4 v4 = *reinterpret_cast<const float4*>(vb + (long)j * p.ldv + 4 * d4);

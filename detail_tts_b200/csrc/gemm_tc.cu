@@ -523,6 +523,8 @@ extern "C" int dtts_gemm_tf32x3(const dtts_gemm_params* p, void* stream) {
   DTTS_REQUIRE((((uintptr_t)p->A_lo) & 15) == 0 && (((uintptr_t)p->W_lo) & 15) == 0, "gemm_tf32x3: low parts must be 16-byte aligned");
   DTTS_REQUIRE(p->split_k <= 1 || (p->out_f32 && p->split_stride >= (int64_t)p->M * p->ldo32), "gemm_tf32x3: split-K needs an fp32 partial buffer of split_k x M x ldo32");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->M > 256 && p->N >= 128) return launch<128, true>(p, st);
+  static int bn128 = -1;
+  if (bn128 < 0) { const char* e = getenv("DTTS_TF32_BN128"); bn128 = e ? atoi(e) : 0; }
+  if ((p->M > 256 || bn128) && p->N >= 128) return launch<128, true>(p, st);
   return launch<64, true>(p, st);
 }

@@ -27,12 +27,15 @@ split_kernel(const dtts_split_params p) {
   }
 }
 
-constexpr int RED_THREADS = 256;
-constexpr int RED_MAXE = 4;   // LayerNorm path: N <= 1024
+constexpr int RED_MAX_THREADS = 1024;
+constexpr int RED_MAXE = 4;   // LayerNorm path: N <= 4 * blockDim.x
 
+// One CTA per row; the CTA is as wide as the row allows (up to 1024 threads) so that the n_splits dependent-latency
+// loads of every column are in flight at once: the kernel is pure latency (a few MB of partials, mostly L2 hits).
 template <bool LN>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_MAX_THREADS)
 reduce_kernel(const dtts_reduce_params p) {
+  const int RED_THREADS = blockDim.x;
   __shared__ float red[40];
   pdl_launch();
   pdl_wait();
@@ -108,11 +111,14 @@ extern "C" int dtts_splitk_reduce(const dtts_reduce_params* p, void* stream) {
   DTTS_REQUIRE(!(p->y_hi && !p->y_lo), "splitk_reduce: y_hi needs y_lo");
   DTTS_REQUIRE(p->act < DTTS_ACT_PAIR_TANH_SIGMOID, "splitk_reduce: pair activations are not supported");
   if (p->M <= 0) return 0;
+  int threads = (p->N + 31) / 32 * 32;
+  if (threads > RED_MAX_THREADS) threads = RED_MAX_THREADS;
+  if (threads < 64) threads = 64;
   if (p->ln_gamma) {
-    DTTS_REQUIRE(p->ln_beta && p->N <= RED_THREADS * RED_MAXE, "splitk_reduce: LayerNorm path needs N <= 1024");
-    launch_maybe_pdl(reduce_kernel<true>, dim3(p->M), dim3(RED_THREADS), 0, (cudaStream_t)stream, *p);
+    DTTS_REQUIRE(p->ln_beta && p->N <= RED_MAX_THREADS * RED_MAXE, "splitk_reduce: LayerNorm path needs N <= 4096");
+    launch_maybe_pdl(reduce_kernel<true>, dim3(p->M), dim3(threads), 0, (cudaStream_t)stream, *p);
   } else {
-    launch_maybe_pdl(reduce_kernel<false>, dim3(p->M), dim3(RED_THREADS), 0, (cudaStream_t)stream, *p);
+    launch_maybe_pdl(reduce_kernel<false>, dim3(p->M), dim3(threads), 0, (cudaStream_t)stream, *p);
   }
   DTTS_CHECK_LAUNCH("splitk_reduce");
   return 0;

@@ -164,8 +164,12 @@ class _DecodeState:
         if gpt.tf32x3:
             xh, xl, ah, al, uh, ul = e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL), e(B, 4 * D_MODEL), e(B, 4 * D_MODEL)
 
-            def splits(pw):      # fill the SMs: (N/64 column tiles) x split_k CTAs
-                return ops.n_splits_for(pw.K, max(1, round(gpt.n_sm / ((pw.N + 63) // 64))))
+            split_div = float(os.environ.get("DTTS_SPLIT_DIV", "1"))
+
+            bn = 128 if os.environ.get("DTTS_TF32_BN128", "0") != "0" else 64
+
+            def splits(pw):      # fill the SMs: (N/bn column tiles) x split_k CTAs
+                return ops.n_splits_for(pw.K, max(1, round(gpt.n_sm / split_div / ((pw.N + bn - 1) // bn))))
             ly0 = T.layers[0]
             S = {k: splits(ly0[k]) for k in ("attn", "proj", "fc", "out")}
             ws = e(max(S[k] * B * ly0[k].N for k in S))
