@@ -27,6 +27,7 @@ RB_K = (3, 7, 11)
 RB_D = (1, 3, 5)
 GAP = 4   # separator rows at frame rate: conv_pre k7 needs 3; x8 upsampling gives >= 25 for k11 d5
 FUSED_MRF = os.environ.get("DTTS_VOC_FUSED", "1") != "0"   # narrow stages (<= 32 padded channels): csrc/voc_fused.cu
+PAD_ROWS = os.environ.get("DTTS_VOC_PAD", "1") != "0"      # wide stages: 128-byte aligned activation rows
 
 
 def _wn(W, p):
@@ -152,14 +153,19 @@ class Generator:
         # cond(g) + conv_pre bias as one per-utterance bias (fp32 GEMV)
         self.cond = pack.pack_linear(W[p + "cond.weight"], W[p + "cond.bias"] + W[p + "conv_pre.bias"], torch.float32, device)
         self.c0 = self.conv_pre.N
-        self.ups, self.res, self.cp, self.mrf = [], [], [], []
+        self.ups, self.res, self.cp, self.mrf, self.ld = [], [], [], [], []
         ch = self.c0
         for i, (u, k) in enumerate(UPS):
             w = _wn(W, p + f"ups.{i}.")                         # [Cin, Cout, k]
-            self.ups.append(pack.pack_conv_transpose1d(w, W[p + f"ups.{i}.bias"], F16, device, stride=u, padding=(k - u) // 2))
             cout = w.shape[1]
             cp = (cout + 7) // 8 * 8
+            # wide stages: rows padded to a multiple of 128 bytes (64 fp16), so that every row of a TMA box is ONE aligned
+            # 128-byte line (208-byte rows made the k=11 convs TMA-request-bound: ~1240 clk per k-block vs 256 of MMA)
+            ld = (cp + 63) // 64 * 64 if (PAD_ROWS and cp > 32) else cp
+            self.ups.append(pack.pack_conv_transpose1d(w, W[p + f"ups.{i}.bias"], F16, device, stride=u, padding=(k - u) // 2,
+                                                       n_pad=ld if ld != cp else 8))
             self.cp.append(cp)
+            self.ld.append(ld)
             blocks = []
             for j, rk in enumerate(RB_K):
                 q = p + f"resblocks.{i * 3 + j}."
@@ -199,9 +205,10 @@ class Generator:
             ops.gemm(z16, pw, out16=x16, act16=ops.ACT_LRELU, act16_param=LRELU_SLOPE, row_utt=lay.row_utt)
         cur = lay
         for i, (u, k) in enumerate(UPS):
-            cp = self.cp[i]
+            cp, ld = self.cp[i], self.ld[i]
             nxt = cur.scaled(u)
-            z = lambda d: torch.zeros(nxt.M, cp, dtype=d, device=dev)  # noqa: E731
+            zf = lambda d: torch.zeros(nxt.M, ld, dtype=d, device=dev)  # noqa: E731  (full padded rows)
+            z = lambda d: zf(d)[:, :cp]  # noqa: E731                    (the cp real/8-padded channels; pad columns stay zero)
             last_slope = LRELU_SLOPE if i < len(UPS) - 1 else 0.01      # F.leaky_relu default, model_24k.py:284
             ru = nxt.row_utt
             if FUSED_MRF and self.mrf[i] is not None:
@@ -213,9 +220,10 @@ class Generator:
                                     slope=LRELU_SLOPE, slope_out=last_slope, out_f16=xs16, ldo16=cp)
                 x16, cur = xs16, nxt
                 continue
-            x32, xl16 = z(torch.float32), z(F16)
-            # polyphase ConvTranspose1d: row t of the GEMM output holds the u upsampled rows t*u..t*u+u-1
-            ops.gemm(x16, self.ups[i], out32=x32.view(cur.M, u * cp), out16=xl16.view(cur.M, u * cp),
+            x32f, xl16f = zf(torch.float32), zf(F16)
+            x32, xl16 = x32f[:, :cp], xl16f[:, :cp]
+            # polyphase ConvTranspose1d: row t of the GEMM output holds the u upsampled rows t*u..t*u+u-1 (ld columns each)
+            ops.gemm(x16, self.ups[i], out32=x32f.view(cur.M, u * ld), out16=xl16f.view(cur.M, u * ld),
                      act16=ops.ACT_LRELU, act16_param=LRELU_SLOPE, row_utt=cur.row_utt)
             xs32, xs16, t16, xk32, xk16 = z(torch.float32), z(F16), z(F16), z(torch.float32), z(F16)
             for j, (c1, c2) in enumerate(self.res[i]):

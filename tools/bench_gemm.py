@@ -18,9 +18,16 @@ SHAPES = [  # name, N, K, taps, res, out32, out16
     ("proj 1x1 +res->f32", 768, 768, 1, True, True, False),
     ("cat 1x1 K1536 ->f32", 768, 1536, 1, False, True, False),
     ("out k3 N256 ->f32", 256, 768, 3, False, True, False),
+    ("voc2 k11 C104", 104, 104, 11, True, True, True),        # vocoder stage 2 ResBlock conv (run with M=1163392)
+    ("voc3 k11 C56", 56, 56, 11, True, True, True),           # stage 3 (M=2326784)
+    ("voc1 k11 C200", 200, 200, 11, True, True, True),        # stage 1 (M=290848)
 ]
+ONLY = os.environ.get("ONLY")
+DIL = int(os.environ.get("DIL", 1))
 g = torch.Generator(device=dev).manual_seed(0)
 for name, N, K, taps, res, o32, o16 in SHAPES:
+    if ONLY and not any(name.startswith(o) for o in ONLY.split(",")):
+        continue
     sets = []
     for _ in range(2):
         A = torch.randn(M, K, generator=g, device=dev).half()
@@ -34,7 +41,7 @@ for name, N, K, taps, res, o32, o16 in SHAPES:
 
     def run(i):
         A, W, bias, R, O32, O16, ru = sets[i % 2]
-        L.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2), tap_stride=1,
+        L.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2) * DIL, tap_stride=DIL,
                bias=bias, row_utt=ru, res=R, ldr=N, out_f32=O32, ldo32=N, out_f16=O16, ldo16=N, act=0, alpha=1.0)
     for i in range(3):
         run(i)
