@@ -508,9 +508,22 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   // 1x1 convs are epilogue / HBM-bound and lose 3-5 % to the pair synchronisation, so they stay on single-CTA tiles
   static int pair = -1;
   if (pair < 0) { const char* e = getenv("DTTS_GEMM_PAIR"); pair = e ? atoi(e) : 1; }
-  if (pair && N % 256 == 0 && p->M >= 4096 && (long)p->K * p->taps >= 1536) return launch_pair<256>(p, st);
-  if (bn256 && N % 256 == 0) return launch<256, false>(p, st);
-  if (N % 192 == 0) return launch<192, false>(p, st);
+  // Tile shape by wave quantisation: cost = waves over the SMs x tile width / relative efficiency of the shape.  At the
+  // bench shape (M = 72k rows) the 256-wide shapes win; on a 1/8 shard (M = 9k) 256-wide tiles leave the second wave
+  // 42 % full and the 192-wide shape is ~20 % cheaper.
+  const bool can_pair = pair && N % 256 == 0 && p->M >= 4096 && (long)p->K * p->taps >= 1536;
+  const bool can256 = bn256 && N % 256 == 0, can192 = N % 192 == 0;
+  if ((can_pair || can256) && can192) {
+    const long mt = ceil_div(p->M, BM), mt2 = ceil_div(p->M, 2 * BM);
+    const double c256 = (double)((mt * (N / 256) + g_sm_count - 1) / g_sm_count) * 256.0;
+    const double c192 = (double)((mt * (N / 192) + g_sm_count - 1) / g_sm_count) * 192.0 / 0.95;
+    const double cpair = (double)((mt2 * (N / 256) + g_sm_count / 2 - 1) / (g_sm_count / 2)) * 256.0 / 1.08;
+    if (c192 < (can256 ? c256 : 1e30) && c192 < (can_pair ? cpair : 1e30)) return launch<192, false>(p, st);
+    if (can_pair && (!can256 || cpair <= c256)) return launch_pair<256>(p, st);
+  }
+  if (can_pair) return launch_pair<256>(p, st);
+  if (can256) return launch<256, false>(p, st);
+  if (can192) return launch<192, false>(p, st);
   if (N > 64) return launch<128, false>(p, st);
   if (N > 32) return launch<64, false>(p, st);
   return launch<32, false>(p, st);

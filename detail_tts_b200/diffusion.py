@@ -27,6 +27,7 @@ from .ops import RowsLayout
 MODEL_CH, HEADS, IN_CH, OUT_CH = 768, 16, 128, 256
 FLASH_IMPL = os.environ.get("DTTS_FLASH", "tc")     # "tc": tcgen05 kernel (attn_tc.cu); "mma": mma.sync kernel (attn_flash.cu)
 FLASH_IMPL = True if FLASH_IMPL == "mma" else "tc"
+GRAPH_MAX_ROWS = int(os.environ.get("DTTS_DIFF_GRAPH_ROWS", "40000"))   # CUDA-graph the eval below this many rows (0 = never)
 F16 = torch.float16
 
 
@@ -318,6 +319,7 @@ class _Engine:
         self.film_idx0 = torch.zeros(nf, dtype=torch.int32, device=dev)
         self.film_idx_utt = _i32([b % layF.n for b in range(nf)], dev)
         self._plans = {}
+        self._graphs, self._runs = {}, {}
 
     def set_state(self, x_bct):
         ops.bct_to_rows(x_bct, self.lay1, dst32=self.x32, dst16=self.x16)
@@ -372,7 +374,27 @@ class _Engine:
             self.film[0].copy_(film)
         if per_utt not in self._plans:
             self._plans[per_utt] = self._record(per_utt)
-        self._plans[per_utt].run()
+        plan = self._plans[per_utt]
+        g = self._graphs.get(per_utt)
+        if g is not None:
+            g.replay()
+            return self.out
+        plan.run()
+        # Small shards (e.g. 16 utterances per GPU at N=8) are launch-bound: ~150 launches of 10-20 us per eval.  Replay the
+        # eval as ONE CUDA graph from the second evaluation on (fixed buffers; the first eager run created every tensor map).
+        if GRAPH_MAX_ROWS and self.lay.M <= GRAPH_MAX_ROWS and per_utt not in self._graphs:
+            self._runs[per_utt] = self._runs.get(per_utt, 0) + 1
+            if self._runs[per_utt] >= 2:
+                graph = torch.cuda.CUDAGraph()
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    graph.capture_begin()
+                    plan.run()
+                    graph.capture_end()
+                cur.wait_stream(side)
+                self._graphs[per_utt] = graph
         return self.out
 
 
