@@ -28,7 +28,8 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2.. epilogue
 constexpr int EPI_LD = 36;        // padded fp32 row of the per-warp 32x32 transpose staging tile
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int EPI_LD_W = 68;      // ... of the 32x64 tile of the fp16-only epilogue (full 128-byte output lines per row)
+constexpr int epi_stage_bytes(int bn, bool tf32) { return EPI_WARPS * 32 * ((bn >= 256 && !tf32) ? EPI_LD_W : EPI_LD) * 4; }
 
 // TF32 = true: 3xTF32 fp32-class GEMM.  Operands are fp32 split on the host side of the ABI into a
 // tf32-exact high part and a low part (x = hi + lo); a stage holds {A_hi, A_lo, W_hi, W_lo} tiles (32 fp32 =
@@ -40,6 +41,7 @@ template <int BN, bool TF32 = false, int CTAS = 1>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // rows of B staged by one CTA x 128 B, for fp16 (64 el) and tf32 (32 el) alike
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
+  static constexpr int EPI_STAGE_BYTES = epi_stage_bytes(BN, TF32);
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = 2 * BN;
@@ -197,7 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ epilogue warps ===============================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int cpar = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks c = cpar, cpar+2, ...
-    float* st = epi_stage + (warp - 2) * 32 * EPI_LD;
+    constexpr bool WIDE_OK = BN >= 256 && !TF32;
+    float* st = epi_stage + (warp - 2) * 32 * (WIDE_OK ? EPI_LD_W : EPI_LD);
     const int cc = (lane & 7) * 4;
     // fast path: plain/act epilogue on 4 consecutive columns per lane, everything 16-byte aligned
     const bool fast = epi.act < DTTS_ACT_PAIR_TANH_SIGMOID && !epi.out_row_map && !epi.accumulate && (epi.N & 3) == 0 &&
@@ -209,6 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // leaky-ReLU on the fp16 copy).  ~25 instructions per 4 outputs: pointers advance by constant strides, row
     // validity comes from a per-tile bitmask loaded while the MMAs still run, all residual loads are issued first.
     const bool lean = fast && epi.act == DTTS_ACT_NONE && (epi.act16 == DTTS_ACT_NONE || epi.act16 == DTTS_ACT_LRELU) && !epi.bias_utt;
+    const bool wide16 = lean && !epi.out_f32 && !epi.res && epi.out_f16 && (epi.ldo16 & 7) == 0 && (((uintptr_t)epi.out_f16) & 15) == 0 &&
+                        (epi.N & 63) == 0 && debug != 4;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = work_id; tile < num_tiles; tile += work_stride) {
       const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
@@ -225,6 +230,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (WIDE_OK && wide16 && debug != 1) {
+        // fp16-only outputs (c1 / qkv convs): 64 columns per pass, a lane owns 8 consecutive columns of a row, so every store
+        // is 16 bytes and 8 lanes write one full 128-byte line (the 32-column path writes half lines from two warps)
+        const int c8 = (lane & 7) * 8;
+        const bool lrelu16 = epi.act16 == DTTS_ACT_LRELU;
+        const float slope = epi.act16_param, alpha = epi.alpha;
+#pragma unroll 1
+        for (int gi = cpar; gi < BN / 64; gi += 2) {
+          const int ng = n0 + gi * 64;
+          if (ng >= epi.N) break;
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            float v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + gi * 64 + hc * 32);
+            tmem_ld32(taddr, v);
+            float4* srow = reinterpret_cast<float4*>(st + lane * EPI_LD_W + hc * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+          __syncwarp();
+          if (debug != 2) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+            if (epi.bias) { ba = __ldg(reinterpret_cast<const float4*>(epi.bias + ng + c8)); bb = __ldg(reinterpret_cast<const float4*>(epi.bias + ng + c8 + 4)); }
+            __half* o16 = epi.out_f16 + (size_t)mrow * epi.ldo16 + ng + c8;
+            const size_t s16 = (size_t)4 * epi.ldo16;
+            const float* sp = st + (lane >> 3) * EPI_LD_W + c8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if ((vmask >> it) & 1u) {
+                const float4 t0 = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD_W);
+                const float4 t1 = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD_W + 4);
+                float w[8] = {t0.x + ba.x, t0.y + ba.y, t0.z + ba.z, t0.w + ba.w, t1.x + bb.x, t1.y + bb.y, t1.z + bb.z, t1.w + bb.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  if (alpha != 1.0f) w[e] *= alpha;
+                  if (lrelu16) w[e] = w[e] > 0.f ? w[e] : w[e] * slope;
+                }
+                __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
+                __half2 h2 = __floats2half2_rn(w[4], w[5]), h3 = __floats2half2_rn(w[6], w[7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o16) = pk;
+              }
+              o16 += s16;
+            }
+          }
+          __syncwarp();
+        }
+      } else
       // TMEM lane = output row.  Each 32x32 chunk is transposed through a per-warp shared-memory tile so that
       // a lane owns 4 CONSECUTIVE columns of a row: residual loads and fp32/fp16 stores are 128 B / 64 B
       // contiguous per row (8 lanes).
@@ -449,7 +504,7 @@ int common_checks(const dtts_gemm_params* p, const char* who, int ld_mult) {
   DTTS_REQUIRE(p->out_f32 || p->out_f16, "%s: no output", who);
   DTTS_REQUIRE(!(p->act >= DTTS_ACT_PAIR_TANH_SIGMOID && (p->N & 1)), "%s: pair activation needs even N", who);
   if (g_debug < 0) {
-    const char* d = getenv("DTTS_GEMM_DEBUG");
+    const char* d = getenv("DTTS_GEMM_DEBUG");   // 1: no epilogue, 2: no global stores, 4: no 64-column fp16 epilogue
     g_debug = d ? atoi(d) : 0;
   }
   if (!g_sm_count) {
