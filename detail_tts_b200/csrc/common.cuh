@@ -106,6 +106,8 @@ struct EpiParams {
   int act, act16;
   float act_param, act16_param, alpha;
   int accumulate;
+  float* gn_stats;   // [n_utt, N/gn_cpg, 2] or nullptr
+  int gn_cpg;
 };
 
 static inline EpiParams make_epi(const dtts_gemm_params* p) {
@@ -116,6 +118,7 @@ static inline EpiParams make_epi(const dtts_gemm_params* p) {
   e.ldr = p->ldr; e.ldo32 = p->ldo32; e.ldo16 = p->ldo16;
   e.act = p->act; e.act16 = p->act16; e.act_param = p->act_param; e.act16_param = p->act16_param;
   e.alpha = p->alpha; e.accumulate = p->accumulate;
+  e.gn_stats = p->gn_stats; e.gn_cpg = p->gn_cpg;
   return e;
 }
 

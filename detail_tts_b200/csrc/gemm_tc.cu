@@ -49,8 +49,48 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
+// GroupNorm statistics of the output tile, accumulated by the epilogue (EpiParams.gn_stats): this lane's per-row partial
+// sums ps / pss (its 4 or 8 columns all lie in group g) for rows mrow + 4*it of utterances uid[it] (-1 = not a row).
+// Utterance ids increase with the row index, so the 32 rows of a warp touch the first utterance, the last one, and
+// (only for utterances shorter than 32 frames) some in between: two shuffle-reduced segments + per-row atomics for the rest.
+__device__ __forceinline__ void gn_accumulate(float* stats, int groups, int g, const int (&uid)[8], const float (&ps)[8],
+                                              const float (&pss)[8], int lane) {
+  int uf = 0x7fffffff, ul = -1;
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    if (uid[it] >= 0) { uf = min(uf, uid[it]); ul = max(ul, uid[it]); }
+  uf = min(uf, __shfl_xor_sync(0xffffffffu, uf, 8)); uf = min(uf, __shfl_xor_sync(0xffffffffu, uf, 16));
+  ul = max(ul, __shfl_xor_sync(0xffffffffu, ul, 8)); ul = max(ul, __shfl_xor_sync(0xffffffffu, ul, 16));
+  if (ul < 0) return;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int u = uid[it];
+    if (u == uf) { a0 += ps[it]; a1 += pss[it]; }
+    else if (u == ul) { b0 += ps[it]; b1 += pss[it]; }
+    else if (u >= 0) {
+      atomicAdd(stats + ((size_t)u * groups + g) * 2, ps[it]);
+      atomicAdd(stats + ((size_t)u * groups + g) * 2 + 1, pss[it]);
+    }
+  }
+  a0 += __shfl_xor_sync(0xffffffffu, a0, 8); a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 8); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+  if (lane < 8) {
+    atomicAdd(stats + ((size_t)uf * groups + g) * 2, a0);
+    atomicAdd(stats + ((size_t)uf * groups + g) * 2 + 1, a1);
+  }
+  if (ul != uf) {   // warp-uniform
+    b0 += __shfl_xor_sync(0xffffffffu, b0, 8); b0 += __shfl_xor_sync(0xffffffffu, b0, 16);
+    b1 += __shfl_xor_sync(0xffffffffu, b1, 8); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+    if (lane < 8) {
+      atomicAdd(stats + ((size_t)ul * groups + g) * 2, b0);
+      atomicAdd(stats + ((size_t)ul * groups + g) * 2 + 1, b1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ the kernel
-template <int BN, bool TF32, int CTAS = 1>
+template <int BN, bool TF32, int CTAS = 1, bool GN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
@@ -212,6 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // leaky-ReLU on the fp16 copy).  ~25 instructions per 4 outputs: pointers advance by constant strides, row
     // validity comes from a per-tile bitmask loaded while the MMAs still run, all residual loads are issued first.
     const bool lean = fast && epi.act == DTTS_ACT_NONE && (epi.act16 == DTTS_ACT_NONE || epi.act16 == DTTS_ACT_LRELU) && !epi.bias_utt;
+    if (GN && !lean) __trap();     // the statistics are only accumulated by the lean epilogue: refuse instead of silently skipping them
     const bool wide16 = lean && !epi.out_f32 && !epi.res && epi.out_f16 && (epi.ldo16 & 7) == 0 && (((uintptr_t)epi.out_f16) & 15) == 0 &&
                         (epi.N & 63) == 0 && debug != 4;
     int acc = 0; uint32_t acc_phase = 0;
@@ -220,14 +261,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * BN;
       const int mrow = m0 + q * 32 + (lane >> 3);   // + it*4
       uint32_t vmask = 0;
+      int uid[8];          // utterance of row mrow + 4*it (only needed for the GroupNorm statistics)
       if (lean) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = mrow + it * 4;
-          const bool ok = m < epi.M && (!epi.row_utt || __ldg(epi.row_utt + m) >= 0);
-          vmask |= ok ? (1u << it) : 0u;
+          const int u = m < epi.M ? (epi.row_utt ? __ldg(epi.row_utt + m) : 0) : -1;
+          uid[it] = u;
+          vmask |= u >= 0 ? (1u << it) : 0u;
         }
       }
+      const bool gn = GN && lean && epi.gn_stats != nullptr;     // GN = false instantiations carry none of the statistics code
+      const int gn_groups = gn ? epi.N / epi.gn_cpg : 0;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (WIDE_OK && wide16 && debug != 1) {
@@ -256,8 +301,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __half* o16 = epi.out_f16 + (size_t)mrow * epi.ldo16 + ng + c8;
             const size_t s16 = (size_t)4 * epi.ldo16;
             const float* sp = st + (lane >> 3) * EPI_LD_W + c8;
+            float ps[8], pss[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
+              ps[it] = 0.f; pss[it] = 0.f;
               if ((vmask >> it) & 1u) {
                 const float4 t0 = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD_W);
                 const float4 t1 = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD_W + 4);
@@ -265,6 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   if (alpha != 1.0f) w[e] *= alpha;
+                  if (GN) { ps[it] += w[e]; pss[it] = fmaf(w[e], w[e], pss[it]); }
                   if (lrelu16) w[e] = w[e] > 0.f ? w[e] : w[e] * slope;
                 }
                 __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
@@ -276,6 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               o16 += s16;
             }
+            if (gn) gn_accumulate(epi.gn_stats, gn_groups, (ng + c8) / epi.gn_cpg, uid, ps, pss, lane);
           }
           __syncwarp();
         }
@@ -318,13 +367,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float* sp = st + (lane >> 3) * EPI_LD + cc;
             const bool lrelu16 = epi.act16 == DTTS_ACT_LRELU;
             const float slope = epi.act16_param, alpha = epi.alpha;
+            float ps[8], pss[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
+              ps[it] = 0.f; pss[it] = 0.f;
               if ((vmask >> it) & 1u) {
                 const float4 t = *reinterpret_cast<const float4*>(sp + it * 4 * EPI_LD);
                 float w0 = t.x + b4.x, w1 = t.y + b4.y, w2 = t.z + b4.z, w3 = t.w + b4.w;
                 if (epi.res) { w0 += rs[it].x; w1 += rs[it].y; w2 += rs[it].z; w3 += rs[it].w; }
                 if (alpha != 1.0f) { w0 *= alpha; w1 *= alpha; w2 *= alpha; w3 *= alpha; }
+                if (GN) {
+                  ps[it] = (w0 + w1) + (w2 + w3);
+                  pss[it] = fmaf(w0, w0, fmaf(w1, w1, fmaf(w2, w2, w3 * w3)));
+                }
                 if (o32) *reinterpret_cast<float4*>(o32) = make_float4(w0, w1, w2, w3);
                 if (o16) {
                   if (lrelu16) {
@@ -341,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (o32) o32 += s32;
               if (o16) o16 += s16;
             }
+            if (gn) gn_accumulate(epi.gn_stats, gn_groups, n / epi.gn_cpg, uid, ps, pss, lane);
           }
         } else {
 #pragma unroll 1
@@ -413,12 +469,12 @@ int g_sm_count = 0;
 int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
 // CTA-pair (cta_group::2) launch: fp16 only, 256 x BN tiles, one 2-CTA cluster per tile stream
-template <int BN>
+template <int BN, bool GN = false>
 int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   using C = Cfg<BN, false, 2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, 2, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc pair<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -441,19 +497,19 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2>, ma, mw, ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2, GN>, ma, mw, ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
                                       kb_all, (long)0, g_debug);
   if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc pair launch failed: %s", cudaGetErrorString(le));
   DTTS_CHECK_LAUNCH("gemm_tc_pair");
   return 0;
 }
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, bool GN = false>
 int launch(const dtts_gemm_params* p, cudaStream_t st) {
   using C = Cfg<BN, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, 1, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -483,11 +539,11 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
   }
   dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
   if (TF32) {
-    cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, e, p->K, p->taps,
+    cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32, 1, GN>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, e, p->K, p->taps,
                                       p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
     if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc launch failed: %s", cudaGetErrorString(le));
   } else {
-    gemm_tc_kernel<BN, TF32><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+    gemm_tc_kernel<BN, TF32, 1, GN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
                                                                         kb_per, (long)p->split_stride, g_debug);
   }
   DTTS_CHECK_LAUNCH("gemm_tc");
@@ -503,6 +559,10 @@ int common_checks(const dtts_gemm_params* p, const char* who, int ld_mult) {
   DTTS_REQUIRE(!(p->bias_utt && !p->row_utt), "%s: bias_utt requires row_utt", who);
   DTTS_REQUIRE(p->out_f32 || p->out_f16, "%s: no output", who);
   DTTS_REQUIRE(!(p->act >= DTTS_ACT_PAIR_TANH_SIGMOID && (p->N & 1)), "%s: pair activation needs even N", who);
+  DTTS_REQUIRE(!p->gn_stats || (p->row_utt && p->gn_cpg > 0 && p->gn_cpg % 8 == 0 && p->N % p->gn_cpg == 0 && p->act == DTTS_ACT_NONE &&
+                                (p->act16 == DTTS_ACT_NONE || p->act16 == DTTS_ACT_LRELU) && !p->bias_utt && !p->out_row_map && !p->accumulate &&
+                                (p->N & 3) == 0),
+               "%s: gn_stats needs row_utt, gn_cpg %% 8 == 0 and the plain bias/residual epilogue", who);
   if (g_debug < 0) {
     const char* d = getenv("DTTS_GEMM_DEBUG");   // 1: no epilogue, 2: no global stores, 4: no 64-column fp16 epilogue
     g_debug = d ? atoi(d) : 0;
@@ -566,6 +626,7 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   // Tile shape by wave quantisation: cost = waves over the SMs x tile width / relative efficiency of the shape.  At the
   // bench shape (M = 72k rows) the 256-wide shapes win; on a 1/8 shard (M = 9k) 256-wide tiles leave the second wave
   // 42 % full and the 192-wide shape is ~20 % cheaper.
+  const bool gs = p->gn_stats != nullptr;
   const bool can_pair = pair && N % 256 == 0 && p->M >= 4096 && (long)p->K * p->taps >= 1536;
   const bool can256 = bn256 && N % 256 == 0, can192 = N % 192 == 0;
   if ((can_pair || can256) && can192) {
@@ -573,12 +634,13 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
     const double c256 = (double)((mt * (N / 256) + g_sm_count - 1) / g_sm_count) * 256.0;
     const double c192 = (double)((mt * (N / 192) + g_sm_count - 1) / g_sm_count) * 192.0 / 0.95;
     const double cpair = (double)((mt2 * (N / 256) + g_sm_count / 2 - 1) / (g_sm_count / 2)) * 256.0 / 1.08;
-    if (c192 < (can256 ? c256 : 1e30) && c192 < (can_pair ? cpair : 1e30)) return launch<192, false>(p, st);
-    if (can_pair && (!can256 || cpair <= c256)) return launch_pair<256>(p, st);
+    if (c192 < (can256 ? c256 : 1e30) && c192 < (can_pair ? cpair : 1e30)) return gs ? launch<192, false, true>(p, st) : launch<192, false>(p, st);
+    if (can_pair && (!can256 || cpair <= c256)) return gs ? launch_pair<256, true>(p, st) : launch_pair<256>(p, st);
   }
-  if (can_pair) return launch_pair<256>(p, st);
-  if (can256) return launch<256, false>(p, st);
-  if (can192) return launch<192, false>(p, st);
+  if (can_pair) return gs ? launch_pair<256, true>(p, st) : launch_pair<256>(p, st);
+  if (can256) return gs ? launch<256, false, true>(p, st) : launch<256, false>(p, st);
+  if (can192) return gs ? launch<192, false, true>(p, st) : launch<192, false>(p, st);
+  DTTS_REQUIRE(!gs, "gemm_f16_tc: gn_stats is implemented for N %% 192 == 0 or N %% 256 == 0");
   if (N > 64) return launch<128, false>(p, st);
   if (N > 32) return launch<64, false>(p, st);
   return launch<32, false>(p, st);

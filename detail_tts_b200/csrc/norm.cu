@@ -546,6 +546,111 @@ groupnorm_cluster_kernel(const T* __restrict__ x, int C, int cpg, int groups, co
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Apply half of GroupNorm32 when the producing GEMM accumulated the statistics (dtts_gemm_params.gn_stats): one fully
+// coalesced elementwise pass.  A CTA owns a 64-row tile and ALL channels: thread -> fixed 8-channel column (its gamma /
+// beta / FiLM coefficients stay in registers), rows strided over the row lanes; A, B are refreshed when the utterance
+// of the row changes.  16-byte fp16 stores: 8 lanes write one full 128-byte line.
+constexpr int GNA_ROWS = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(384, sizeof(T) == 4 ? 2 : 3)
+groupnorm_apply_kernel(const dtts_gn_apply_params p) {
+  const int C8 = p.C >> 3;                       // 8-channel vectors per row
+  const int rl = blockDim.x / C8;                // row lanes
+  const int col = threadIdx.x % C8, rlane = threadIdx.x / C8;
+  if (rlane >= rl) return;
+  const int c = col * 8, g = c / p.cpg, G = p.C / p.cpg;
+  float A_[8], B_[8];
+  int cur = -1;
+  const int m_end = min(p.M, (int)(blockIdx.x + 1) * GNA_ROWS);
+  constexpr int NB = sizeof(T) == 4 ? 3 : 4;     // rows in flight per thread (the pass is pure streaming: latency is hidden by loads in flight)
+  for (int base = blockIdx.x * GNA_ROWS + rlane; base < m_end; base += NB * rl) {
+    int us[NB];
+    uint4 raw[NB][sizeof(T) == 4 ? 2 : 1];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int m = base + j * rl;
+      us[j] = m < m_end ? __ldg(p.row_utt + m) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (us[j] < 0) continue;
+      const size_t m = (size_t)(base + j * rl);
+      if (sizeof(T) == 4) {
+        raw[j][0] = __ldcs(reinterpret_cast<const uint4*>((const float*)p.x + m * p.ldx + c));
+        raw[j][sizeof(T) == 4 ? 1 : 0] = __ldcs(reinterpret_cast<const uint4*>((const float*)p.x + m * p.ldx + c + 4));
+      } else {
+        raw[j][0] = __ldcs(reinterpret_cast<const uint4*>((const __half*)p.x + m * p.ldx + c));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int u = us[j];
+      if (u < 0) continue;
+      const size_t m = (size_t)(base + j * rl);
+      if (u != cur) {
+        cur = u;
+        const float2 st = *reinterpret_cast<const float2*>(p.stats + ((size_t)u * G + g) * 2);
+        const float inv_n = 1.0f / ((float)__ldg(p.utt_len + u) * p.cpg);
+        const float mean = st.x * inv_n;
+        const float rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + p.eps);
+#pragma unroll
+        for (int q = 0; q < 8; q += 4) {           // (gamma / beta are re-read only when the utterance changes)
+          const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c + q), be = *reinterpret_cast<const float4*>(p.beta + c + q);
+          A_[q] = rstd * ga.x; A_[q + 1] = rstd * ga.y; A_[q + 2] = rstd * ga.z; A_[q + 3] = rstd * ga.w;
+          B_[q] = be.x - mean * A_[q]; B_[q + 1] = be.y - mean * A_[q + 1]; B_[q + 2] = be.z - mean * A_[q + 2]; B_[q + 3] = be.w - mean * A_[q + 3];
+        }
+        if (p.film_scale) {   // (x*A+B)*(1+fs)+fb
+          const long fr = p.film_idx ? p.film_idx[u] : u;
+#pragma unroll
+          for (int q = 0; q < 8; q += 4) {
+            const float4 fs = *reinterpret_cast<const float4*>(p.film_scale + fr * p.ld_film + c + q);
+            const float4 fb = *reinterpret_cast<const float4*>(p.film_shift + fr * p.ld_film + c + q);
+            const float f1[4] = {1.f + fs.x, 1.f + fs.y, 1.f + fs.z, 1.f + fs.w}, f0[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { A_[q + k] *= f1[k]; B_[q + k] = B_[q + k] * f1[k] + f0[k]; }
+          }
+        }
+      }
+      float y[8];
+      if (sizeof(T) == 4) {
+        const uint4 v0 = raw[j][0], v1 = raw[j][sizeof(T) == 4 ? 1 : 0];
+        y[0] = __uint_as_float(v0.x); y[1] = __uint_as_float(v0.y); y[2] = __uint_as_float(v0.z); y[3] = __uint_as_float(v0.w);
+        y[4] = __uint_as_float(v1.x); y[5] = __uint_as_float(v1.y); y[6] = __uint_as_float(v1.z); y[7] = __uint_as_float(v1.w);
+      } else {
+        const uint32_t w[4] = {raw[j][0].x, raw[j][0].y, raw[j][0].z, raw[j][0].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+          y[2 * k] = t.x; y[2 * k + 1] = t.y;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y[q] = fmaf(y[q], A_[q], B_[q]);
+      if (p.act == DTTS_ACT_SILU) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = silu_fast(y[q]);
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(p.out_f32 + m * p.ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out_f32 + m * p.ldo32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (p.out_f16) {
+        __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+        __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>((__half*)p.out_f16 + m * p.ldo16 + c) = pk;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_f32_kernel(float* p, long n) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) p[i] = 0.f;
+}
+
 constexpr int LN_MAXE = 32;  // C <= 1024
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
@@ -740,6 +845,37 @@ extern "C" int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream) {
         (const float*)p->x, p->ldx, p->C, cpg, p->utt_off, p->utt_len, p->gamma, p->beta, p->film_scale, p->film_shift,
         p->ld_film, p->film_idx, p->act, p->eps, p->out_f32, p->ldo32, (__half*)p->out_f16, p->ldo16, cache_rows);
   DTTS_CHECK_LAUNCH("groupnorm");
+  return 0;
+}
+
+extern "C" int dtts_groupnorm_apply(const dtts_gn_apply_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->x && p->row_utt && p->utt_len && p->stats && p->gamma && p->beta, "groupnorm_apply: null argument");
+  DTTS_REQUIRE(p->C % 8 == 0 && p->cpg > 0 && p->cpg % 8 == 0 && p->C % p->cpg == 0 && p->C / 8 <= 384, "groupnorm_apply: needs C %% 8 == 0, cpg %% 8 == 0, C <= 3072");
+  DTTS_REQUIRE(p->out_f32 || p->out_f16, "groupnorm_apply: no output");
+  DTTS_REQUIRE(p->act == DTTS_ACT_NONE || p->act == DTTS_ACT_SILU, "groupnorm_apply: unsupported activation");
+  const int es = p->x_is_f16 ? 2 : 4;
+  DTTS_REQUIRE((((uintptr_t)p->x) & 15) == 0 && (p->ldx * es) % 16 == 0 && ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta) | ((uintptr_t)p->stats)) & 15) % 8 == 0 &&
+               ((((uintptr_t)p->gamma) | ((uintptr_t)p->beta)) & 15) == 0, "groupnorm_apply: operands must be 16-byte aligned");
+  DTTS_REQUIRE(!p->film_scale || (((((uintptr_t)p->film_scale) | ((uintptr_t)p->film_shift)) & 15) == 0 && p->ld_film % 4 == 0), "groupnorm_apply: FiLM rows must be 16-byte aligned");
+  DTTS_REQUIRE(!p->out_f16 || ((((uintptr_t)p->out_f16) & 15) == 0 && p->ldo16 % 8 == 0), "groupnorm_apply: fp16 output must be 16-byte aligned");
+  DTTS_REQUIRE(!p->out_f32 || ((((uintptr_t)p->out_f32) & 15) == 0 && p->ldo32 % 4 == 0), "groupnorm_apply: fp32 output must be 16-byte aligned");
+  if (p->M <= 0) return 0;
+  const int C8 = p->C / 8;
+  const int threads = (384 / C8) * C8;
+  const int grid = ceil_div(p->M, GNA_ROWS);
+  if (p->x_is_f16) groupnorm_apply_kernel<__half><<<grid, threads, 0, (cudaStream_t)stream>>>(*p);
+  else groupnorm_apply_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(*p);
+  DTTS_CHECK_LAUNCH("groupnorm_apply");
+  return 0;
+}
+
+extern "C" int dtts_zero_f32(const dtts_zero_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->ptr && p->n >= 0, "zero_f32: bad argument");
+  if (p->n == 0) return 0;
+  long g = (p->n + 255) / 256;
+  if (g > 1184) g = 1184;
+  zero_f32_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p->ptr, (long)p->n);
+  DTTS_CHECK_LAUNCH("zero_f32");
   return 0;
 }
 

@@ -27,6 +27,7 @@ from .ops import RowsLayout
 MODEL_CH, HEADS, IN_CH, OUT_CH = 768, 16, 128, 256
 FLASH_IMPL = os.environ.get("DTTS_FLASH", "tc")     # "tc": tcgen05 kernel (attn_tc.cu); "mma": mma.sync kernel (attn_flash.cu)
 FLASH_IMPL = True if FLASH_IMPL == "mma" else "tc"
+FUSE_GN_STATS = os.environ.get("DTTS_GN_FUSED", "1") != "0"   # GroupNorm statistics in the producing GEMM's epilogue
 GRAPH_MAX_ROWS = int(os.environ.get("DTTS_DIFF_GRAPH_ROWS", "40000"))   # CUDA-graph the eval below this many rows (0 = never)
 F16 = torch.float16
 
@@ -80,6 +81,25 @@ class _Buf:
         self.qkv = z(3 * C, F16)
 
 
+class _StatsPool:
+    """Zeroed GroupNorm statistics buffers [n_utt, 32, 2] for the GEMM epilogues of one recorded eval: one slab, handed out
+    in order while the plan is recorded and cleared by ONE launch at the start of every eval."""
+
+    def __init__(self, n_utt_max, count, device):
+        self.stride = n_utt_max * 32 * 2
+        self.buf = torch.zeros(count * self.stride, dtype=torch.float32, device=device)
+        self.used = 0
+
+    def take(self, lay):
+        assert lay.n * 64 <= self.stride and (self.used + 1) * self.stride <= self.buf.numel(), "statistics pool exhausted"
+        v = self.buf[self.used * self.stride:self.used * self.stride + lay.n * 64]
+        self.used += 1
+        return v
+
+    def clear(self):
+        ops._lib.lib().call("dtts_zero_f32", ptr=self.buf, n=self.used * self.stride)
+
+
 class DiffusionTts:
     def __init__(self, W, device="cuda", p="diffusion."):
         self.device = dev = torch.device(device)
@@ -107,24 +127,38 @@ class DiffusionTts:
         self._film_cache = {}
 
     # ---- building blocks on rows ---------------------------------------------------------------
-    def _attn_block(self, at, x32, lay, buf, out16=None):
+    # `st_in` / `sp` thread GroupNorm statistics through the blocks: st_in = the (sum, sum of squares) buffer that the GEMM
+    # which PRODUCED the block's input filled in its epilogue (None: compute them here with the standalone kernel); sp = a
+    # pool handing out zeroed [n_utt, 32, 2] buffers (None: fusion off).  Each block returns the statistics of its output.
+    def _gn(self, x, lay, norm, st_in, **kw):
+        if st_in is None:
+            ops.groupnorm(x, lay, *norm, **kw)
+        else:
+            ops.groupnorm_apply(x, lay, st_in, *norm, **kw)
+
+    def _attn_block(self, at, x32, lay, buf, out16=None, st_in=None, sp=None):
         """x32 += proj(attention(qkv(GN(x32))))  (in place); optional fp16 copy of the result."""
         C, ch = at.C, at.ch
         ru = lay.row_utt
-        ops.groupnorm(x32, lay, *at.norm, out16=buf.g)
+        self._gn(x32, lay, at.norm, st_in, out16=buf.g)
         ops.gemm(buf.g, at.qkv, out16=buf.qkv, row_utt=ru)
         ops.attention(buf.qkv, buf.qkv[:, ch:], buf.qkv[:, 2 * ch:], HEADS, ch, lay.off, lay.len, lay.off, lay.len,
                       lay.max_len, lay.max_len, ch ** -0.5, out16=buf.a, head_stride=3 * ch, bias_table=at.bias,
                       bias_half=64, flash=FLASH_IMPL if ch == 48 else False)
-        ops.gemm(buf.a, at.proj, res=x32, out32=x32, out16=out16, row_utt=ru)
+        st_out = sp.take(lay) if sp is not None else None
+        ops.gemm(buf.a, at.proj, res=x32, out32=x32, out16=out16, row_utt=ru, gn_stats=st_out, gn_cpg=C // 32)
+        return st_out
 
-    def _res_block(self, rb, x_in, x_out, lay, buf, film, film_idx):
+    def _res_block(self, rb, x_in, x_out, lay, buf, film, film_idx, st_in=None, sp=None):
         """x_out = x_in + conv_k3(SiLU(FiLM(GN(conv1x1(SiLU(GN(x_in)))))))"""
         ru = lay.row_utt
-        ops.groupnorm(x_in, lay, *rb.n1, out16=buf.g, act=ops.ACT_SILU)
-        ops.gemm(buf.g, rb.c1, out16=buf.h, row_utt=ru)
-        ops.groupnorm(buf.h, lay, *rb.n2, out16=buf.g, film=film, film_idx=film_idx, act=ops.ACT_SILU)
-        ops.gemm(buf.g, rb.c2, res=x_in, out32=x_out, row_utt=ru)
+        self._gn(x_in, lay, rb.n1, st_in, out16=buf.g, act=ops.ACT_SILU)
+        st_h = sp.take(lay) if sp is not None else None
+        ops.gemm(buf.g, rb.c1, out16=buf.h, row_utt=ru, gn_stats=st_h, gn_cpg=MODEL_CH // 32)
+        self._gn(buf.h, lay, rb.n2, st_h, out16=buf.g, film=film, film_idx=film_idx, act=ops.ACT_SILU)
+        st_out = sp.take(lay) if sp is not None else None
+        ops.gemm(buf.g, rb.c2, res=x_in, out32=x_out, row_utt=ru, gn_stats=st_out, gn_cpg=MODEL_CH // 32)
+        return st_out
 
     # ---- timestep FiLM ----------------------------------------------------------------------------
     def film_table(self, timesteps):
@@ -329,19 +363,23 @@ class _Engine:
         ru, M = lay.row_utt, self.M
         fidx = self.film_idx_utt if per_utt else self.film_idx0
         L = ops._lib.lib()
+        sp = _StatsPool(max(lay.n, self.lay_i.n), 3 * len(m.resblocks) + 2, self.m.device) if FUSE_GN_STATS else None
         with L.record() as plan:
             r = 0
             src = self.ce0
             lay_i = self.lay_i
             buf_i = self.buf_i if self.both else buf
             assert not (self.both and per_utt), "per-utterance timesteps are only supported for single-branch evals"
+            if sp is not None:
+                L.call("dtts_zero_f32", ptr=sp.buf, n=sp.buf.numel())
+            st = None          # statistics of `src` (None for the constant code embedding: standalone GroupNorm)
             for i, (rb, at) in enumerate(m.integrator):
-                self.m._res_block(rb, src, self.c32, lay_i, buf_i, self.film[:, r], fidx)
+                st = self.m._res_block(rb, src, self.c32, lay_i, buf_i, self.film[:, r], fidx, st_in=st, sp=sp)
                 last = i == len(m.integrator) - 1
                 dst16 = None
                 if last:
                     dst16 = self.ci16 if self.both else self.cat[:, MODEL_CH:]
-                self.m._attn_block(at, self.c32, lay_i, buf_i, out16=dst16)
+                st = self.m._attn_block(at, self.c32, lay_i, buf_i, out16=dst16, st_in=st, sp=sp)
                 src = self.c32
                 r += 1
             if self.both:
@@ -350,16 +388,18 @@ class _Engine:
             ops.gemm(self.x16, m.inp_block, out16=self.cat[:M, :MODEL_CH], row_utt=self.lay1.row_utt)
             if self.both:
                 ops.gemm(self.x16, m.inp_block, out16=self.cat[M:, :MODEL_CH], row_utt=self.lay1.row_utt)
-            ops.gemm(self.cat, m.integrating_conv, out32=self.h32, row_utt=ru)
+            st = sp.take(lay) if sp is not None else None
+            ops.gemm(self.cat, m.integrating_conv, out32=self.h32, row_utt=ru, gn_stats=st, gn_cpg=MODEL_CH // 32)
             for rb, at in m.layers:
-                self.m._res_block(rb, self.h32, self.h32, lay, buf, self.film[:, r], fidx)
-                self.m._attn_block(at, self.h32, lay, buf)
+                st = self.m._res_block(rb, self.h32, self.h32, lay, buf, self.film[:, r], fidx, st_in=st, sp=sp)
+                st = self.m._attn_block(at, self.h32, lay, buf, st_in=st, sp=sp)
                 r += 1
             for rb in m.tail:
-                self.m._res_block(rb, self.h32, self.h32, lay, buf, self.film[:, r], fidx)
+                st = self.m._res_block(rb, self.h32, self.h32, lay, buf, self.film[:, r], fidx, st_in=st, sp=sp)
                 r += 1
-            ops.groupnorm(self.h32, lay, *m.out_norm, out16=buf.g, act=ops.ACT_SILU)
+            self.m._gn(self.h32, lay, m.out_norm, st, out16=buf.g, act=ops.ACT_SILU)
             ops.gemm(buf.g, m.out_conv, out32=self.out, row_utt=ru)
+        plan.keep.append(sp)
         return plan
 
     def eval(self, film, per_utt=False):

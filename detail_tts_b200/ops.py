@@ -70,7 +70,7 @@ def split_tf32(x, hi, lo):
 
 def gemm(A, pw, out32=None, out16=None, res=None, act=ACT_NONE, act_param=0.0, act16=ACT_NONE,
          act16_param=0.0, alpha=1.0, accumulate=False, row_utt=None, bias_utt=None, out_row_map=None,
-         M=None, bias=True):
+         M=None, bias=True, gn_stats=None, gn_cpg=0):
     """out = alpha*(act(sum_taps A[m+shift] @ W_t^T + bias [+ bias_utt[row_utt]]) + res)."""
     L = _lib.lib()
     fn = "dtts_gemm_f16_tc" if A.dtype == torch.float16 else "dtts_gemm_f32"
@@ -83,7 +83,19 @@ def gemm(A, pw, out32=None, out16=None, res=None, act=ACT_NONE, act_param=0.0, a
            out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
            out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0,
            act=act, act16=act16, act_param=act_param, act16_param=act16_param, alpha=alpha,
-           accumulate=int(accumulate))
+           accumulate=int(accumulate), gn_stats=gn_stats, gn_cpg=gn_cpg if gn_stats is not None else 0)
+
+
+def groupnorm_apply(x, lay, stats, gamma, beta, out32=None, out16=None, groups=32, film=None, film_idx=None, act=ACT_NONE,
+                    eps=1e-5):
+    """GroupNorm32 whose statistics [n_utt, groups, 2] were accumulated by the GEMM that produced x (gn_stats)."""
+    C = gamma.numel()
+    _lib.lib().call("dtts_groupnorm_apply", x=x, x_is_f16=int(x.dtype == torch.float16), ldx=_ld(x), M=x.shape[0], C=C,
+                    cpg=C // groups, row_utt=lay.row_utt, utt_len=lay.len, stats=stats, gamma=gamma, beta=beta,
+                    film_scale=film, film_shift=film[:, C:] if film is not None else None,
+                    ld_film=_ld(film) if film is not None else 0, film_idx=film_idx, act=act, eps=eps,
+                    out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
+                    out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0)
 
 
 def groupnorm(x, lay, gamma, beta, out32=None, out16=None, groups=32, film=None, film_idx=None, act=ACT_NONE,

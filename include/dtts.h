@@ -62,6 +62,9 @@ typedef struct {
   const void* W_lo;       /* same for W */
   int split_k;            /* > 1: K is split over split_k CTAs per tile; raw partial sums are written to        */
   int64_t split_stride;   /*   out_f32 + s*split_stride (elements) and bias/act/res/out_f16 are ignored          */
+  /* dtts_gemm_f16_tc only: GroupNorm statistics of the OUTPUT, accumulated by the epilogue (needs row_utt): */
+  float* gn_stats;        /* [n_utt, N/gn_cpg, 2] (sum, sum of squares) += over this launch's rows; NULL = off */
+  int gn_cpg;             /* channels per group (multiple of 8) */
 } dtts_gemm_params;
 
 /* D = epilogue(sum_taps A[m+shift_t,:] . W_t[n,:]) on tcgen05 tensor cores (fp16 operands, fp32
@@ -95,6 +98,23 @@ typedef struct {
 /* GroupNorm32 (fp32 statistics over channels-in-group x frames of ONE utterance) + optional
  * timestep FiLM + SiLU: vqvae/utils/diff_util.py:113-133, vqvae/diff_model.py:107,113-115,242. */
 int dtts_groupnorm(const dtts_groupnorm_params* p, void* stream);
+
+typedef struct {
+  const void* x; int x_is_f16; int ldx;   /* [M, C] */
+  int M, C, cpg;
+  const int* row_utt;                      /* [M]: utterance of each row, -1 = separator (not written) */
+  const int* utt_len;                      /* [n_utt] frames per utterance (statistics are over utt_len * cpg values) */
+  const float* stats;                      /* [n_utt, C/cpg, 2] (sum, sum of squares) from the producing GEMM (gn_stats) */
+  const float* gamma; const float* beta;
+  const float* film_scale; const float* film_shift; int ld_film; const int* film_idx;
+  int act; float eps;
+  float* out_f32; int ldo32; void* out_f16; int ldo16;
+} dtts_gn_apply_params;
+/* The apply half of GroupNorm32 when the statistics were accumulated by the epilogue of the GEMM that produced x
+ * (dtts_gemm_params.gn_stats): one fully coalesced pass, y = (x - mean) * rstd * gamma + beta (+FiLM) (+SiLU). */
+int dtts_groupnorm_apply(const dtts_gn_apply_params* p, void* stream);
+typedef struct { float* ptr; int64_t n; } dtts_zero_params;
+int dtts_zero_f32(const dtts_zero_params* p, void* stream);    /* ptr[0..n) = 0 (statistics buffers, inside a launch plan) */
 
 typedef struct {
   const float* x; int ldx; int M, C;

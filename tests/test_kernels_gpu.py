@@ -187,6 +187,48 @@ def test_groupnorm(dlib, C, film, act, f16):
     assert o32[:2].abs().max().item() == 0  # separator rows untouched
 
 
+@pytest.mark.parametrize("M_scale,N,K,taps,res", [(1, 768, 768, 1, False), (1, 768, 768, 3, True), (20, 768, 768, 3, True),
+                                                  (20, 768, 1536, 1, False)])
+def test_gemm_gn_stats_and_apply(dlib, M_scale, N, K, taps, res):
+    """GroupNorm statistics accumulated by the GEMM epilogue (gn_stats) + dtts_groupnorm_apply == torch group_norm of the
+    GEMM output per utterance.  Ragged utterances incl. shorter than one 32-row epilogue strip; the large case runs the
+    cta_group::2 tiles; fp16-only output exercises the 64-column epilogue."""
+    lens = [37, 280, 5, 1, 64] * M_scale
+    off, ln, M = _layout(lens, 1)
+    n_utt = len(lens)
+    g = torch.Generator(device=DEV).manual_seed(N + K + taps)
+    A = torch.randn(M, K, generator=g, device=DEV).half()
+    W = (torch.randn(taps * N, K, generator=g, device=DEV) / math.sqrt(K * taps)).half()
+    bias = torch.randn(N, generator=g, device=DEV)
+    ru = torch.full((M,), -1, dtype=torch.int32, device=DEV)
+    for b, n in enumerate(lens):
+        A[int(off[b]) + n:int(off[b]) + n + 1] = 0
+        ru[int(off[b]):int(off[b]) + n] = b
+    A[:1] = 0
+    R = torch.randn(M, N, generator=g, device=DEV) if res else None
+    stats = torch.zeros(n_utt, 32, 2, device=DEV)
+    o32 = torch.zeros(M, N, device=DEV) if res else None
+    o16 = torch.zeros(M, N, device=DEV, dtype=torch.float16) if not res else None
+    dlib.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2), tap_stride=1,
+              bias=bias, row_utt=ru, res=R, ldr=N, out_f32=o32, ldo32=N, out_f16=o16, ldo16=N, act=0, alpha=1.0,
+              gn_stats=stats, gn_cpg=N // 32)
+    y = o32 if res else o16
+    gamma, beta = torch.randn(N, generator=g, device=DEV), torch.randn(N, generator=g, device=DEV)
+    out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+    dlib.call("dtts_groupnorm_apply", x=y, x_is_f16=int(not res), ldx=N, M=M, C=N, cpg=N // 32, row_utt=ru, utt_len=ln,
+              stats=stats, gamma=gamma, beta=beta, act=L.ACT_SILU, eps=1e-5, out_f16=out, ldo16=N)
+    for b, n in list(enumerate(lens))[:7]:
+        sl = slice(int(off[b]), int(off[b]) + n)
+        yb = y[sl].float()
+        # statistics: sum / sum of squares of the (unrounded) outputs per group
+        sref = yb.reshape(n, 32, N // 32).double()
+        assert torch.allclose(stats[b, :, 0].double(), sref.sum((0, 2)), rtol=2e-3, atol=2e-2 * n ** 0.5), b
+        assert torch.allclose(stats[b, :, 1].double(), sref.pow(2).sum((0, 2)), rtol=2e-3, atol=1e-2), b
+        r = torch.nn.functional.silu(torch.nn.functional.group_norm(yb.t()[None], 32, gamma, beta, 1e-5))[0].t()
+        assert (out[sl].float() - r).abs().max().item() < 2e-2, b
+    assert out[~(ru >= 0)].abs().max().item() == 0
+
+
 def test_layernorm(dlib):
     M, C = 77, 768
     g = torch.Generator(device=DEV).manual_seed(1)
