@@ -79,6 +79,29 @@ def metrics(src, dst, comments):
             w.writerow([i, per[key]["kernel"]] + [per[key].get(n, "") for n in names])
 
 
+def traffic(src, dst, comments):
+    """per-launch metrics CSV (the `metrics` mode's output) -> the JSON bench.py's roofline.traffic is read from."""
+    import json
+    rows = list(csv.DictReader(l for l in open(src) if not l.startswith("#")))
+    col = lambda key: next(c for c in rows[0] if c.startswith(key))
+    rd, wr, tm, tp = (col(k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
+                                         "sm__pipe_tensor_cycles_active"))
+    tot_r = sum(float(r[rd]) for r in rows)
+    tot_w = sum(float(r[wr]) for r in rows)
+    tot_t = sum(float(r[tm]) for r in rows)
+    out = {
+        "kernel": "gemm_tc_kernel",
+        "launches": len(rows),
+        "dram_bytes_per_launch": (tot_r + tot_w) / len(rows),
+        "dram_read_bytes_total": tot_r,
+        "dram_write_bytes_total": tot_w,
+        "ncu_time_us_total": tot_t / 1e3,
+        "tensor_pipe_pct_time_weighted": sum(float(r[tp]) * float(r[tm]) for r in rows) / tot_t,
+        "source": " ".join(comments),
+    }
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
-    {"launches": launches, "full": full, "metrics": metrics}[mode](src, dst, sys.argv[4:])
+    {"launches": launches, "full": full, "metrics": metrics, "traffic": traffic}[mode](src, dst, sys.argv[4:])
