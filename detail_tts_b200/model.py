@@ -14,6 +14,7 @@ from . import synth
 from .diffusion import DiffusionTts, SpacedDiffusion, denormalize_torch_mel, do_spectrogram_diffusion, space_timesteps
 from .flowvae import FlowVAE
 from .gpt import STOP_MEL, UnifiedVoice
+from .vqpath import VQDecoder
 
 
 class SynthesizerTrn:
@@ -30,6 +31,8 @@ class SynthesizerTrn:
         self.flowvae = FlowVAE(W, self.device)
         self.ref_enc, self.enc_p, self.flow, self.dec = (self.flowvae.ref_enc, self.flowvae.enc_p, self.flowvae.flow,
                                                          self.flowvae.dec)
+        # the diffusion-free branch (infer_gpt, model_24k.py:811-847) needs the VQ tensors; checkpoints always hold them
+        self.vq = VQDecoder(W, self.device) if "vq_dec.1.weight" in W else None
         self.capture_latents = True     # take the diffusion latents from the decode steps
 
     def eval(self):
@@ -38,6 +41,29 @@ class SynthesizerTrn:
     def to(self, device):
         assert torch.device(device).type == "cuda"
         return self
+
+    def _generate_codes(self, text, text_lengths, refer, refer_lengths, max_generate_length, do_sample, suppress_eos, hooks):
+        """The GPT sampling call both `infer` and `infer_gpt` start with (model_24k.py:782-795 / :819-831) and the
+        per-utterance code counts a B=1 run of the reference would have produced (`codes[:, :-1]`)."""
+        dev = self.device
+        B = text.shape[0]
+        tl = [int(v) for v in text_lengths]
+        rl = [int(v) for v in refer_lengths]
+        refer = refer.to(dev, torch.float32)
+        kw = dict(do_sample=do_sample, repetition_penalty=2.0, num_return_sequences=1,
+                  max_generate_length=max_generate_length, text_lengths=tl, multinomial=hooks.get("multinomial"))
+        if do_sample:
+            kw.update(top_p=.8, temperature=.8, length_penalty=1.0)         # model_24k.py:786-791
+        if suppress_eos:
+            kw["suppress_tokens"] = [STOP_MEL]
+        codes = self.gpt.inference_speech_tortoise(refer, rl, text, **kw)
+        # model_24k.py:795: codes[:, :-1] drops the stop token (or the last token when the cap was hit)
+        G = codes.shape[1]
+        fin = codes == STOP_MEL
+        first_stop = torch.where(fin.any(1), fin.float().argmax(1), torch.full((B,), G, device=dev))
+        gen_len = torch.clamp(first_stop + 1, max=G)              # tokens HF would have emitted for a B=1 run
+        T = [int(v) - 1 for v in gen_len.tolist()]
+        return codes, T, tl, rl, refer
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -59,24 +85,9 @@ class SynthesizerTrn:
                 e.record()
                 marks.append((name, e))
         mark("start")
-        B = text.shape[0]
-        tl = [int(v) for v in text_lengths]
-        rl = [int(v) for v in refer_lengths]
-        refer = refer.to(dev, torch.float32)
-        kw = dict(do_sample=do_sample, repetition_penalty=2.0, num_return_sequences=1,
-                  max_generate_length=max_generate_length, text_lengths=tl, multinomial=hooks.get("multinomial"))
-        if do_sample:
-            kw.update(top_p=.8, temperature=.8, length_penalty=1.0)         # model_24k.py:786-791
-        if suppress_eos:
-            kw["suppress_tokens"] = [STOP_MEL]
-        codes = self.gpt.inference_speech_tortoise(refer, rl, text, **kw)
+        codes, T, tl, rl, refer = self._generate_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample,
+                                                       suppress_eos, hooks)
         mark("gpt")
-        # model_24k.py:795: codes[:, :-1] drops the stop token (or the last token when the cap was hit)
-        G = codes.shape[1]
-        fin = codes == STOP_MEL
-        first_stop = torch.where(fin.any(1), fin.float().argmax(1), torch.full((B,), G, device=dev))
-        gen_len = torch.clamp(first_stop + 1, max=G)              # tokens HF would have emitted for a B=1 run
-        T = [int(v) - 1 for v in gen_len.tolist()]
         assert min(T) >= 1, "an utterance produced no codes"
         Tmax = max(T)
         codes = codes[:, :Tmax]
@@ -108,6 +119,30 @@ class SynthesizerTrn:
         """vqvae/model_24k.py:774-810: batch item 0 only, returns wav [1,1,1024*T]."""
         wav, wl = self.infer_batch(text[:1], [int(text_length[0])] if text_length is not None else [text.shape[1]],
                                    refer[:1], [int(refer_lengths[0])], noise_scale=noise_scale, **kw)
+        return wav[:, :, :int(wl[0])]
+
+    @torch.no_grad()
+    def infer_gpt_batch(self, text, text_lengths, refer, refer_lengths, noise_scale=0.667, max_generate_length=600,
+                        do_sample=True, suppress_eos=False, hooks=None, trace=None):
+        """Batched SynthesizerTrn.infer_gpt (model_24k.py:811-847): GPT codes -> codebook decode + vq_ref_enc -> vq_dec
+        -> infer_flowvae; no diffusion.  Same arguments and return convention as `infer_batch`; an utterance whose
+        first token is the stop token yields the reference's 16 zero-latent codes (:835-836)."""
+        if self.vq is None:
+            raise RuntimeError("this checkpoint holds no quantizer / vq_dec / vq_ref_enc tensors (infer_gpt branch)")
+        hooks = hooks or {}
+        codes, T, tl, rl, refer = self._generate_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample,
+                                                       suppress_eos, hooks)
+        recon, y_lengths = self.vq.forward(codes, T, refer, rl)                 # model_24k.py:831-844
+        wav = self.flowvae.infer(recon, y_lengths, noise_scale=noise_scale, randn_like=hooks.get("randn_like_zp"))
+        if trace is not None:
+            trace.update(codes=codes, T=T, recon=recon)
+        return wav, torch.tensor([256 * n for n in y_lengths], device=self.device)
+
+    @torch.no_grad()
+    def infer_gpt(self, text, text_length, refer, refer_lengths, noise_scale=0.667, **kw):
+        """vqvae/model_24k.py:811-847: batch item 0 only, returns wav [1,1,1024*T]."""
+        wav, wl = self.infer_gpt_batch(text[:1], [int(text_length[0])] if text_length is not None else [text.shape[1]],
+                                       refer[:1], [int(refer_lengths[0])], noise_scale=noise_scale, **kw)
         return wav[:, :, :int(wl[0])]
 
     @torch.no_grad()

@@ -55,6 +55,8 @@ def _draw(key, shape, seed, sd):
             return torch.ones(shape)
         if key.endswith("cluster_size"):
             return torch.ones(shape)
+        if key.endswith(("_codebook.embed", "project_out.weight")):
+            return randn(0.6)   # decoded latents O(1), comparable to the vq_ref_enc style vector they are added to
         return randn(0.1)
     if last == "weight_g":
         # weight-norm gain: g = ||v|| * (1 + 5% jitter) so the effective weight is ~v
@@ -126,11 +128,12 @@ def synth_state_dict(seed=0, keys=None):
     return out
 
 
-INFER_PREFIXES = ("gpt.", "diffusion.", "dec.", "flow.", "enc_p.", "ref_enc.", "in_proj.")
+INFER_PREFIXES = ("gpt.", "diffusion.", "dec.", "flow.", "enc_p.", "ref_enc.", "in_proj.",
+                  "quantizer.vq.layers.0._codebook.embed", "quantizer.vq.layers.0.project_out.", "vq_dec.", "vq_ref_enc.")
 
 
 def infer_path_key(k):
-    """True for tensors reached from SynthesizerTrn.infer (vqvae/model_24k.py:774-810)."""
+    """True for tensors reached from SynthesizerTrn.infer / infer_gpt (vqvae/model_24k.py:774-847)."""
     if not k.startswith(INFER_PREFIXES):
         return False
     if k.startswith("gpt.inference_model."):

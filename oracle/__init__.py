@@ -10,7 +10,7 @@ tokenizer ids) is input prep, checked in tests/test_oracle_golden.py.
 """
 import torch
 
-from . import diffusion, flowvae, frontend, gpt  # noqa: F401
+from . import diffusion, flowvae, frontend, gpt, vqpath  # noqa: F401
 
 
 def infer(W, text, refer, refer_lengths, sched=None, max_generate_length=600, do_sample=True,

@@ -100,6 +100,23 @@ def test_pack_conv_transpose1d(cin, cout, k, u):
     assert (up - ref.double()).abs().max() < 2e-4
 
 
+def test_pack_conv_transpose1d_vq_dec_shape():
+    """vq_dec's ConvTranspose1d(k=3, stride=2, padding=1, output_padding=1) (model_24k.py:620-624): exactly 2T rows."""
+    g = torch.Generator().manual_seed(5)
+    w, b = torch.randn(16, 8, 3, generator=g), torch.randn(8, generator=g)
+    T = 11
+    x = torch.randn(1, 16, T, generator=g)
+    ref = F.conv_transpose1d(x, w, b, stride=2, padding=1, output_padding=1)[0].t()     # [2T, cout]
+    pw = pack.pack_conv_transpose1d(w, b, torch.float32, "cpu", stride=2, padding=1)
+    gap = 2
+    rows = torch.zeros(T + 2 * gap, pw.K)
+    rows[gap:gap + T, :16] = x[0].t()
+    out = gemm_emul(rows, pw)
+    up = out.reshape(-1, pw.N // 2)[gap * 2:(gap + T) * 2, :8]
+    assert up.shape == ref.shape
+    assert (up - ref.double()).abs().max() < 2e-4
+
+
 def test_pack_conv1d_stride2():
     g = torch.Generator().manual_seed(3)
     w, b = torch.randn(14, 6, 3, generator=g), torch.randn(14, generator=g)

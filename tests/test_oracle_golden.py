@@ -137,3 +137,18 @@ def test_frontend_oracle_matches_reference_melspec():
         mel = ofe.mel_spectrogram(item["wav"])
         assert mel.shape == item["mel"].shape, name
         assert float((mel - item["mel"]).abs().max()) < 2e-4, name
+
+
+def test_vqpath_oracle_matches_reference(weights):
+    """infer_gpt's deterministic tail (codebook decode + vq_ref_enc + vq_dec + infer_flowvae, model_24k.py:831-847)
+    against the unmodified reference's outputs (tests/golden/make_vqpath.py), incl. the empty-latent case."""
+    import oracle.vqpath as ovq
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vqpath.pt"))
+    for b, T in enumerate(fx["code_lengths"].tolist()):
+        rl = fx["refer_lengths"][b:b + 1]
+        rf = fx["refer"][b:b + 1, :, :int(rl)]
+        torch.manual_seed(fx["seeds"][b])
+        recon, wav = ovq.infer_gpt_from_codes(weights, fx["codes"][b:b + 1, :T], rf, rl)
+        assert recon.shape == fx["recon"][b].shape and wav.shape == fx["wav"][b].shape
+        assert (recon - fx["recon"][b]).abs().max() < 1e-5
+        assert (wav - fx["wav"][b]).pow(2).mean().sqrt() < 1e-6

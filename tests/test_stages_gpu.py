@@ -282,3 +282,54 @@ def test_frontend_melspec_matches_reference():
         one, fr1 = fe(wav[b:b + 1, :n].to(DEV))
         assert frames[b] == fr1[0] == n // 256
         assert torch.equal(mel_b[b, :, :frames[b]], one[0])
+
+
+def _vq_fixture():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "vqpath.pt"), map_location="cpu")
+
+
+def test_infer_gpt_tail_matches_reference(model):
+    """SURVEY.md 8f rank 2, infer_gpt (model_24k.py:831-847): codebook decode + vq_ref_enc + vq_dec on the ragged batch
+    (13, 7 and 0 codes: the last is the reference's empty-latent case) against the unmodified reference's outputs;
+    then infer_flowvae per utterance with the reference's noise draw.  Budgets: mel 1e-3 RMS (relative to the mel's
+    0.31 RMS), waveform 1e-4 RMS."""
+    fx = _vq_fixture()
+    T = fx["code_lengths"].tolist()
+    recon, ylen = model.vq.forward(fx["codes"].to(DEV), T, fx["refer"].to(DEV), fx["refer_lengths"].tolist())
+    assert ylen == [4 * (t if t > 0 else 16) for t in T]
+    for b, n in enumerate(ylen):
+        e = rms(recon[b:b + 1, :, :n], fx["recon"][b])
+        print("vq_dec mel rms err", e, "of", float(fx["recon"][b].pow(2).mean().sqrt()))
+        assert e < 1e-3, e
+        assert n == recon.shape[2] or recon[b, :, n:].abs().max().item() == 0
+        torch.manual_seed(fx["seeds"][b])
+        wav = model.infer_flowvae(recon[b:b + 1, :, :n], torch.tensor([n]), None, randn_like=CPU_HOOKS["randn_like_zp"])
+        ew = rms(wav, fx["wav"][b])
+        print("infer_gpt wav rms err", ew, "of", float(fx["wav"][b].pow(2).mean().sqrt()))
+        assert ew < 1e-4, ew
+
+
+def test_infer_gpt_end_to_end_matches_oracle(model, weights):
+    """infer_gpt from text: sampled codes (token-exact, the reference's RNG order) -> VQ branch -> waveform, against the
+    CPU oracle; and the batched call equals the B=1 calls."""
+    import oracle.gpt as og
+    import oracle.vqpath as ovq
+    g = torch.Generator().manual_seed(77)
+    text = torch.nn.functional.pad(torch.randint(3, 255, (1, 12), generator=g, dtype=torch.int32), (0, 1))
+    refer = (torch.randn(1, 128, 40, generator=g) * 2 - 5).clamp(-11.5, 2.7)
+    rl = torch.tensor([40])
+    G = 9
+    torch.manual_seed(3)
+    wav = model.infer_gpt(text, [13], refer.to(DEV), [40], max_generate_length=G, hooks=CPU_HOOKS)
+    torch.manual_seed(3)
+    codes = og.generate(weights, refer, rl, text, max_generate_length=G, do_sample=True)
+    codes = codes[:, :-1]
+    stop = (codes[0] == 8193).nonzero()
+    if len(stop):
+        codes = codes[:, :int(stop[0])]
+    _, owav = ovq.infer_gpt_from_codes(weights, codes, refer, rl)
+    assert wav.shape == owav.shape, (wav.shape, owav.shape)
+    e = rms(wav, owav)
+    print("infer_gpt e2e wav rms err", e)
+    assert e < 1e-4, e
