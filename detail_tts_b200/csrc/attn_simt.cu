@@ -278,35 +278,59 @@ int launch_tile(const dtts_attention_params* p, cudaStream_t st) {
 }
 
 // ---- KV-cache decode attention: ONE query per (utterance, head) against its cached keys/values.
-// One warp per (utterance, head), 4 heads per CTA.  Phase 1: 4 lanes share a key (each 3 x float4 of the
-// 48-dim row, 64 B contiguous per key per load), 8 keys per warp iteration, scores to shared memory.
-// Phase 2: 12 lanes x float4 cover a value row (192 B coalesced), two lane groups take even/odd keys and
-// are combined in a fixed order.  fp32 throughout; bit-reproducible.
+// The step is latency-bound (ten dependent launches per token), so the kernel is organised for memory-level parallelism:
+// one CTA of 4 warps per (utterance, head); the keys are dealt to the warps 8 at a time, so that at 125 cached positions
+// every key row (phase 1) and every value row (phase 2) of the head is in flight at once.
+// Phase 1: 4 lanes share a key (3 x float4 of the 48-dim row each), 8 keys per warp iteration, scores to shared memory.
+// Phase 2: 8 lanes x 6 floats cover a value row, 4 keys per warp iteration; lane groups, then warps, are combined in a
+// fixed order.  fp32 throughout; bit-reproducible.  Optionally starts by reducing the split-K partials of the new
+// token's q|k|v columns (dtts_attention_params.qkv_ws).
 constexpr int DEC_WARPS = 4;
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attention_decode_kernel(const dtts_attention_params p) {
-  extern __shared__ float sm[];
+  extern __shared__ float sm[];          // [max_k_len] scores
+  __shared__ __align__(16) float qs[48];
+  __shared__ float red[2 * DEC_WARPS];
+  __shared__ __align__(16) float part[DEC_WARPS][48];
   pdl_launch();
   pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x * DEC_WARPS + warp, b = blockIdx.y;
-  if (h >= p.n_heads || p.q_len[b] <= 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (p.q_len[b] <= 0) return;
   const int nk = p.k_len[b];
   if (nk <= 0) return;
-  float* sc = sm + warp * p.max_k_len;
-  const float* q = (const float*)p.q + (long)p.q_off[b] * p.ldq + (long)h * p.head_stride_q;
+  const long arow = (long)p.q_off[b];
+  const float* q = (const float*)p.q + arow * p.ldq + (long)h * p.head_stride_q;
   const float* kb = (const float*)p.k + (long)p.k_off[b] * p.ldk + (long)h * p.head_stride_k;
   const float* vb = (const float*)p.v + (long)p.k_off[b] * p.ldv + (long)h * p.head_stride_v;
+  if (p.qkv_ws) {
+    // fused split-K reduce of this head's new q|k|v columns (same arithmetic and order as reduce_kernel, gpt_step.cu)
+    const int width = p.n_heads * 48;
+    const float* wsr = p.qkv_ws + (long)b * p.qkv_ld_ws;
+    for (int c = tid; c < 3 * 48; c += DEC_WARPS * 32) {
+      const int prt = c / 48, d = c - prt * 48;
+      const int col = prt * width + h * 48 + d;
+      float v = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < p.qkv_splits; ++k) v += wsr[(long)k * p.qkv_split_stride + col];   // fixed order
+      if (p.qkv_bias) v += __ldg(p.qkv_bias + col);
+      float* dst = prt == 0 ? (float*)p.q + arow * p.ldq + (long)h * p.head_stride_q
+                 : prt == 1 ? (float*)p.k + arow * p.ldk + (long)h * p.head_stride_k
+                            : (float*)p.v + arow * p.ldv + (long)h * p.head_stride_v;
+      dst[d] = v;
+      if (prt == 0) qs[d] = v * p.scale;
+    }
+  } else if (tid < 48) {
+    qs[tid] = q[tid] * p.scale;
+  }
+  __syncthreads();   // q staged; the new key/value row (global) is visible to the whole CTA
   const int sub = lane & 3, kl = lane >> 2;
   float4 q4[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    q4[i] = *reinterpret_cast<const float4*>(q + 16 * i + 4 * sub);
-    q4[i].x *= p.scale; q4[i].y *= p.scale; q4[i].z *= p.scale; q4[i].w *= p.scale;
-  }
+  for (int i = 0; i < 3; ++i) q4[i] = *reinterpret_cast<const float4*>(qs + 16 * i + 4 * sub);
   float lmax = -INFINITY;
 #pragma unroll 4
-  for (int j0 = 0; j0 < nk; j0 += 8) {   // unrolled: the (latency-bound) key loads of 4 iterations are in flight together
+  for (int j0 = warp * 8; j0 < nk; j0 += DEC_WARPS * 8) {
     const int j = j0 + kl;
     float s = 0.f;
     if (j < nk) {
@@ -320,34 +344,56 @@ attention_decode_kernel(const dtts_attention_params p) {
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (j < nk) {
-      if (sub == 0) sc[j] = s;
+      if (sub == 0) sm[j] = s;
       lmax = fmaxf(lmax, s);
     }
   }
   lmax = warp_max(lmax);
-  __syncwarp();
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  const float gmax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   float lsum = 0.f;
-  for (int j = lane; j < nk; j += 32) {
-    const float e = expf(sc[j] - lmax);
-    sc[j] = e;
+  for (int j = tid; j < nk; j += DEC_WARPS * 32) {
+    const float e = expf(sm[j] - gmax);
+    sm[j] = e;
     lsum += e;
   }
-  const float inv = 1.0f / warp_sum(lsum);
-  __syncwarp();
-  const int g2 = lane / 12, d4 = lane % 12;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g2 < 2) {
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[DEC_WARPS + warp] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (((red[DEC_WARPS] + red[DEC_WARPS + 1]) + red[DEC_WARPS + 2]) + red[DEC_WARPS + 3]);
+  // phase 2: lane group g (8 lanes) takes key j0 + g, lane l of the group the dims [6l, 6l+6): all 32 lanes load, 16 keys
+  // per CTA iteration, unrolled so that every value row of the head is in flight at once (measured: 31 us vs 41 us for the
+  // 12-lanes-x-float4 mapping at 128 utterances x 125 positions)
+  const int g = lane >> 3, l6 = (lane & 7) * 6;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-    for (int j = g2; j < nk; j += 2) {
-      const float pj = sc[j];
-      const float4 v4 = *reinterpret_cast<const float4*>(vb + (long)j * p.ldv + 4 * d4);
-      acc.x = fmaf(pj, v4.x, acc.x); acc.y = fmaf(pj, v4.y, acc.y); acc.z = fmaf(pj, v4.z, acc.z); acc.w = fmaf(pj, v4.w, acc.w);
+  for (int j0 = warp * 4; j0 < nk; j0 += DEC_WARPS * 4) {
+    const int j = j0 + g;
+    if (j < nk) {
+      const float pj = sm[j];
+      const float2* vj = reinterpret_cast<const float2*>(vb + (long)j * p.ldv + l6);
+      const float2 a = vj[0], c = vj[1], e = vj[2];
+      acc[0] = fmaf(pj, a.x, acc[0]); acc[1] = fmaf(pj, a.y, acc[1]); acc[2] = fmaf(pj, c.x, acc[2]);
+      acc[3] = fmaf(pj, c.y, acc[3]); acc[4] = fmaf(pj, e.x, acc[4]); acc[5] = fmaf(pj, e.y, acc[5]);
     }
   }
-  const float ox = __shfl_down_sync(0xffffffffu, acc.x, 12), oy = __shfl_down_sync(0xffffffffu, acc.y, 12);
-  const float oz = __shfl_down_sync(0xffffffffu, acc.z, 12), ow = __shfl_down_sync(0xffffffffu, acc.w, 12);
-  if (lane < 12) {
-    const float4 o = make_float4((acc.x + ox) * inv, (acc.y + oy) * inv, (acc.z + oz) * inv, (acc.w + ow) * inv);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) part[warp][l6 + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < 12) {
+    const int d = 4 * tid;
+    float o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = (((part[0][d + i] + part[1][d + i]) + part[2][d + i]) + part[3][d + i]) * inv;
+    const float4 o = make_float4(o4[0], o4[1], o4[2], o4[3]);
     const long orow = (p.o_off ? p.o_off[b] : p.q_off[b]);
     if (p.out_lo) {   // tf32 operand split for the projection GEMM (dtts_gemm_tf32x3)
       float4 hi, lo;
@@ -355,11 +401,11 @@ attention_decode_kernel(const dtts_attention_params p) {
       hi.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u); lo.y = o.y - hi.y;
       hi.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); lo.z = o.z - hi.z;
       hi.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u); lo.w = o.w - hi.w;
-      *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = hi;
-      *reinterpret_cast<float4*>(p.out_lo + orow * p.ldo_lo + h * 48 + 4 * d4) = lo;
-    } else if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + 4 * d4) = o;
+      *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + d) = hi;
+      *reinterpret_cast<float4*>(p.out_lo + orow * p.ldo_lo + h * 48 + d) = lo;
+    } else if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo32 + h * 48 + d) = o;
     if (p.out_f16) {
-      __half* hp = (__half*)p.out_f16 + orow * p.ldo16 + h * 48 + 4 * d4;
+      __half* hp = (__half*)p.out_f16 + orow * p.ldo16 + h * 48 + d;
       hp[0] = __float2half_rn(o.x); hp[1] = __float2half_rn(o.y); hp[2] = __float2half_rn(o.z); hp[3] = __float2half_rn(o.w);
     }
   }
@@ -386,18 +432,19 @@ extern "C" int dtts_attention_f32(const dtts_attention_params* p, void* stream) 
       p->ldq % 4 == 0 && p->ldk % 4 == 0 && p->ldv % 4 == 0 && p->head_stride_q % 4 == 0 && p->head_stride_k % 4 == 0 &&
       p->head_stride_v % 4 == 0 && ((((uintptr_t)p->q) | ((uintptr_t)p->k) | ((uintptr_t)p->v)) & 15) == 0 &&
       (!p->out_f32 || (p->ldo32 % 4 == 0 && (((uintptr_t)p->out_f32) & 15) == 0)) &&
-      (size_t)DEC_WARPS * p->max_k_len * sizeof(float) <= 200 * 1024) {
+      (size_t)p->max_k_len * sizeof(float) <= 200 * 1024) {
     static bool dec_attr = false;
     if (!dec_attr) {
       cudaFuncSetAttribute(attention_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       dec_attr = true;
     }
-    dim3 grid(ceil_div(p->n_heads, DEC_WARPS), p->n_utt);
-    launch_maybe_pdl(attention_decode_kernel, grid, dim3(DEC_WARPS * 32), (size_t)DEC_WARPS * p->max_k_len * sizeof(float), (cudaStream_t)stream, *p);
+    dim3 grid(p->n_heads, p->n_utt);
+    launch_maybe_pdl(attention_decode_kernel, grid, dim3(DEC_WARPS * 32), (size_t)p->max_k_len * sizeof(float), (cudaStream_t)stream, *p);
     DTTS_CHECK_LAUNCH("attention_decode");
     return 0;
   }
   DTTS_REQUIRE(!p->out_lo, "attention_f32: out_lo (tf32 split) is only produced by the fp32 KV-cache decode path");
+  DTTS_REQUIRE(!p->qkv_ws, "attention_f32: the fused QKV split-K reduce is only available on the fp32 KV-cache decode path");
   if (p->max_q_len > 1 && p->head_dim % 4 == 0 && p->head_dim <= 192 && p->window >= 0 && p->window <= 16) {
     cudaStream_t st = (cudaStream_t)stream;
     const int hd = p->head_dim;

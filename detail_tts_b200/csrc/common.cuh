@@ -37,7 +37,7 @@ extern int g_dtts_launches;
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
-// programmatic dependent launch (PDL) for the latency-bound GPT decode step: the ~94 small kernels of a
+// programmatic dependent launch (PDL) for the latency-bound GPT decode step: the ~84 small kernels of a
 // step are launched with cudaLaunchAttributeProgrammaticStreamSerialization while dtts_set_pdl(1) is in
 // effect, so kernel N+1 is scheduled (and runs its prologue) while kernel N drains.  Every such kernel
 // calls pdl_launch() first and pdl_wait() before it touches memory written by its predecessor; both are

@@ -98,15 +98,35 @@ process_logits_kernel(const dtts_logits_params p) {
       if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t rem = sel_remaining;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (hist[b] >= rem) break;
-        rem -= hist[b];
+    if (tid < 32) {
+      // bucket holding the rem-th largest key: scan the 256 bins from the top, one warp (lane l owns bins 8l..8l+7;
+      // suffix sums over lanes by shuffles) instead of a 256-step dependent loop in one thread
+      const uint32_t rem = sel_remaining;
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c[i] = hist[tid * 8 + i]; tot += c[i]; }
+      uint32_t suf = tot;                       // -> sum over lanes >= tid
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (tid + o < 32) suf += t;
       }
-      sel_prefix = prefix | ((uint32_t)b << shift);
-      sel_remaining = rem;
+      const uint32_t above = suf - tot;         // keys in bins owned by higher lanes
+      const bool mine = above < rem && suf >= rem;
+      const uint32_t who = __ballot_sync(0xffffffffu, mine);
+      if (mine) {
+        uint32_t r = rem - above;
+        int i = 7;
+        for (; i > 0; --i) {
+          if (c[i] >= r) break;
+          r -= c[i];
+        }
+        sel_prefix = prefix | ((uint32_t)(tid * 8 + i) << shift);
+        sel_remaining = r;
+      } else if (who == 0 && tid == 0) {        // fewer than rem keys under this prefix (cannot happen: kept for safety)
+        sel_prefix = prefix;
+        sel_remaining = rem - (suf - c[0]);
+      }
     }
     __syncthreads();
   }

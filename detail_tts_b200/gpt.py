@@ -24,6 +24,8 @@ START_TEXT, STOP_TEXT = 255, 0
 START_MEL, STOP_MEL = 8192, 8193
 N_LAYERS, N_HEADS, D_MODEL, HEAD_DIM = 10, 16, 768, 48
 VOCAB = 8194
+# decode step: the split-K reduce of the QKV GEMM runs inside the attention kernel (one launch less per layer)
+FUSE_QKV_REDUCE = os.environ.get("DTTS_FUSE_QKV", "1") != "0"
 
 
 def _i32(x, device):
@@ -202,10 +204,14 @@ class _DecodeState:
                 ops.splitk_reduce(None, 0, B, D_MODEL, res=xs, ln=T.layers[0]["ln1"], y_hi=xh, y_lo=xl)
                 for l, ly in enumerate(T.layers):
                     ops.gemm_tf32x3(xh, xl, ly["attn"], wsv["attn"], split_k=S["attn"])
-                    ops.splitk_reduce(wsv["attn"], S["attn"], B, 3 * D_MODEL, bias=ly["attn"].bias, out32=arena[l],
-                                      out_row_map=kv_row)
+                    fuse = FUSE_QKV_REDUCE and ly["attn"].N == 3 * D_MODEL
+                    if not fuse:
+                        ops.splitk_reduce(wsv["attn"], S["attn"], B, 3 * D_MODEL, bias=ly["attn"].bias, out32=arena[l],
+                                          out_row_map=kv_row)
+                    # (fused: each (utterance, head) warp of the attention kernel reduces its own q|k|v columns into the arena)
                     ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row,
-                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=ah, out_lo=al)
+                                  ones, k_off, kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=ah, out_lo=al,
+                                  **({"qkv_ws": wsv["attn"], "qkv_bias": ly["attn"].bias} if fuse else {}))
                     ops.gemm_tf32x3(ah, al, ly["proj"], wsv["proj"], split_k=S["proj"])
                     ops.splitk_reduce(wsv["proj"], S["proj"], B, D_MODEL, bias=ly["proj"].bias, res=xs, out32=xs,
                                       ln=ly["ln2"], y_hi=xh, y_lo=xl)

@@ -120,7 +120,7 @@ def layernorm(x, gamma, beta, out32=None, out16=None, res=None, M=None, eps=1e-5
 
 def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max_k, scale, out32=None, out16=None,
               head_stride=None, causal=False, causal_offset=None, bias_table=None, bias_half=0, rel_k=None,
-              rel_v=None, window=0, o_off=None, flash=False, out_lo=None):
+              rel_v=None, window=0, o_off=None, flash=False, out_lo=None, qkv_ws=None, qkv_bias=None):
     L = _lib.lib()
     hs = head_dim if head_stride is None else head_stride
     mode = BIAS_RELPOS_TABLE if bias_table is not None else (BIAS_WINDOW_REL if rel_k is not None else BIAS_NONE)
@@ -133,7 +133,11 @@ def attention(q, k, v, n_heads, head_dim, q_off, q_len, k_off, k_len, max_q, max
            bias_half=bias_half, rel_k=rel_k, rel_v=rel_v, window=window,
            out_f32=out32, ldo32=_ld(out32) if out32 is not None else 0,
            out_f16=out16, ldo16=_ld(out16) if out16 is not None else 0, o_off=o_off,
-           out_lo=out_lo, ldo_lo=_ld(out_lo) if out_lo is not None else 0)
+           out_lo=out_lo, ldo_lo=_ld(out_lo) if out_lo is not None else 0,
+           # decode fast path: qkv_ws [splits, B, 3*n_heads*head_dim] split-K partials of the new token's QKV row
+           qkv_ws=qkv_ws, qkv_splits=qkv_ws.shape[0] if qkv_ws is not None else 0,
+           qkv_split_stride=qkv_ws.stride(0) if qkv_ws is not None else 0,
+           qkv_ld_ws=qkv_ws.stride(1) if qkv_ws is not None else 0, qkv_bias=qkv_bias)
 
 
 def bct_to_rows(src, lay, dst32=None, dst16=None, scale=1.0, shift=0.0):

@@ -145,6 +145,12 @@ typedef struct {
   const int* o_off;           /* [n_utt] first output row of utterance b; NULL = q_off */
   float* out_lo; int ldo_lo;  /* decode fast path only: out_f32 receives the tf32-exact high part, out_lo the low part */
   int n_rows;                 /* dtts_attention_f16_tc only: rows of the q / k / v buffers (bounds of the TMA tensor maps) */
+  /* decode fast path only (optional): the new token's q|k|v row is still the split-K partials of the QKV GEMM.
+   * Each (utterance, head) warp first reduces its own 3*head_dim columns -- sum over qkv_splits in fixed order, + qkv_bias,
+   * exactly dtts_splitk_reduce's arithmetic -- and stores them at row q_off[b] of q, k and v (column slices of one KV
+   * arena whose newest key row is q_off[b]); saves the reduce launch of every layer of the latency-bound decode step.
+   * Partials: qkv_ws[s*qkv_split_stride + b*qkv_ld_ws + part*n_heads*head_dim + h*head_dim + d], part = 0 q, 1 k, 2 v. */
+  const float* qkv_ws; int qkv_splits; int64_t qkv_split_stride; int qkv_ld_ws; const float* qkv_bias;
 } dtts_attention_params;
 /* softmax(scale*q.k + bias) v in exact fp32 on CUDA cores, one query per CTA.  Covers the small
  * attentions: GPT-2 causal attention incl. KV-cache decode (modeling_gpt2.py:54-72),
