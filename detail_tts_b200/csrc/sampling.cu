@@ -1,5 +1,5 @@
 // sampling.cu -- the per-token host-free tail of the GPT decode step.
-//   dtts_process_logits: HF processor chain RepetitionPenalty -> Temperature -> TopK -> TopP ->
+//   dtts_process_logits: HF processor chain RepetitionPenalty -> [Typical] -> Temperature -> TopK -> TopP ->
 //     softmax (or argmax when greedy): transformers generation/logits_process.py:298,407-410,
 //     522-532,582-585, as configured by vqvae/model_24k.py:782-792 / gpt/model.py:540-544.
 //   dtts_append_token: HF _sample bookkeeping (generation/utils.py:2797-2805) fused with the next
@@ -56,6 +56,44 @@ process_logits_kernel(const dtts_logits_params p) {
   __syncthreads();
   if (p.suppress_token >= 0 && p.suppress_token < V && tid == 0) sh[p.suppress_token] = -INFINITY;
   __syncthreads();
+
+  if (p.typical_mass > 0.f) {
+    // TypicalLogitsWarper (gpt/modules/typical_sampling.py:14-33): keep the tokens whose surprise -log p is closest to the
+    // entropy, up to cumulative probability `mass`.  The reference sorts |(-log p) - H| ascending, takes the value at the
+    // first sorted index whose cumulative probability reaches the mass and removes everything above it; that value is the
+    // smallest t with sum{p_i : shifted_i <= t} >= mass, found here by a 32-step bisection over the (order-preserving) bit
+    // pattern of the non-negative shifted scores, every step one deterministic block reduction.
+    float m = -INFINITY;
+    for (int i = tid; i < V; i += PL_THREADS) m = fmaxf(m, sh[i]);
+    const float mx = block_max(m, red);
+    float z = 0.f;
+    for (int i = tid; i < V; i += PL_THREADS) z += expf(sh[i] - mx);
+    const float Z = block_sum(z, red);
+    const float logZ = mx + logf(Z);
+    float e = 0.f;
+    for (int i = tid; i < V; i += PL_THREADS) {
+      const float lp = sh[i] - logZ;
+      const float pr = expf(lp);
+      if (pr > 0.f) e -= lp * pr;            // nansum: -inf * 0 terms are skipped
+    }
+    const float ent = block_sum(e, red);
+    uint32_t lo = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = lo | ((1u << bit) - 1u);
+      float acc = 0.f;
+      for (int i = tid; i < V; i += PL_THREADS) {
+        const float lp = sh[i] - logZ;
+        const float shifted = fabsf(-lp - ent);
+        if (__float_as_uint(shifted) <= cand) acc += expf(lp);
+      }
+      if (block_sum(acc, red) < p.typical_mass) lo |= 1u << bit;
+    }
+    for (int i = tid; i < V; i += PL_THREADS) {
+      const float shifted = fabsf(-(sh[i] - logZ) - ent);
+      if (__float_as_uint(shifted) > lo) sh[i] = -INFINITY;
+    }
+    __syncthreads();
+  }
 
   if (!p.do_sample) {
     // argmax, lowest index on ties

@@ -134,7 +134,7 @@ class _DecodeState:
     is what makes it capturable into ONE CUDA graph and replayable with no per-token marshalling."""
 
     def __init__(self, gpt, B, Pmax, G, sampling):
-        do_sample, penalty, temperature, top_p, top_k, suppress_token = sampling
+        do_sample, penalty, temperature, top_p, top_k, suppress_token, typical_mass = sampling
         self.gpt, self.B, self.G = gpt, B, G
         dev, dt = gpt.device, gpt.dtype
         self.stride = stride = Pmax + 1 + G                  # KV arena rows per utterance
@@ -190,7 +190,8 @@ class _DecodeState:
                 ops.gemm(hdt if dt == torch.float16 else hn, gpt.mel_head, out32=self.logits)
             lib.call("dtts_process_logits", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
                      n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
-                     do_sample=int(do_sample), suppress_token=suppress_token, probs=self.probs, ldp=VOCAB, argmax=self.argmax)
+                     do_sample=int(do_sample), suppress_token=suppress_token, probs=self.probs, ldp=VOCAB, argmax=self.argmax,
+                     typical_mass=typical_mass)
 
         with lib.record() as self.head_plan:
             head()
@@ -435,9 +436,11 @@ class UnifiedVoice:
         after EOS), as HF generate()[:, trunc_index:] does.  Supported generate kwargs are the ones the
         reference passes (vqvae/model_24k.py:782-792): do_sample, top_p, temperature, top_k (HF
         default 50), repetition_penalty, length_penalty (ignored when sampling, as in HF),
-        suppress_tokens=[8193].  `multinomial(probs)->[B,1]` overrides torch.multinomial (tests)."""
-        assert input_tokens is None and num_return_sequences == 1 and not typical_sampling, \
-            "only the configuration SynthesizerTrn.infer uses is implemented"
+        suppress_tokens=[8193]; `typical_sampling=True` inserts the reference's TypicalLogitsWarper(mass=typical_mass)
+        (gpt/modules/typical_sampling.py) after the repetition penalty, where HF puts custom processors.
+        `multinomial(probs)->[B,1]` overrides torch.multinomial (tests)."""
+        assert input_tokens is None and num_return_sequences == 1, \
+            "input_tokens / num_return_sequences > 1 are not implemented"
         kw = dict(hf_generate_kwargs)
         do_sample = bool(kw.pop("do_sample", False))
         top_p = float(kw.pop("top_p", 1.0))
@@ -462,7 +465,8 @@ class UnifiedVoice:
         start = torch.full((B, 1), START_MEL, dtype=torch.long, device=dev)
         x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, start, [1] * B)
         Pmax = max(P)
-        st = self._decode_state(B, Pmax, G, (do_sample, penalty, temperature, top_p, top_k, suppress_token))
+        st = self._decode_state(B, Pmax, G, (do_sample, penalty, temperature, top_p, top_k, suppress_token,
+                                             float(typical_mass) if typical_sampling else 0.0))
         st.reset(P)
         y = self._trunk_rows(x, seq_off, seq_len, st.arena, st.stride)
 

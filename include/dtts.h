@@ -174,10 +174,12 @@ typedef struct {
   int do_sample; int suppress_token;             /* -1 = none */
   float* probs; int ldp;                         /* do_sample: dense probabilities [n_rows, vocab] */
   int64_t* argmax;                               /* greedy: [n_rows] */
+  float typical_mass;                            /* > 0: TypicalLogitsWarper(mass) between the penalty and the temperature */
 } dtts_logits_params;
-/* HF processor chain RepetitionPenalty -> Temperature -> TopK -> TopP -> softmax (or argmax):
+/* HF processor chain RepetitionPenalty -> [TypicalLogitsWarper] -> Temperature -> TopK -> TopP -> softmax (or argmax):
  * transformers generation/logits_process.py:298,407-410,522-532,582-585 as driven by
- * vqvae/model_24k.py:782-792 / gpt/model.py:540-544. */
+ * vqvae/model_24k.py:782-792 / gpt/model.py:540-544; the optional typical warper is the reference's own
+ * gpt/modules/typical_sampling.py:5-33 (custom processors run after the penalty and before the sampling warpers). */
 int dtts_process_logits(const dtts_logits_params* p, void* stream);
 
 typedef struct {

@@ -175,11 +175,32 @@ def top_p_filter(scores, top_p, min_keep=1):
     return scores.masked_fill(rm, float("-inf"))
 
 
+def typical_filter(scores, mass=0.9):
+    """gpt/modules/typical_sampling.py:14-33 (TypicalLogitsWarper, min_tokens_to_keep=1): keep the tokens whose
+    surprise is closest to the entropy until their cumulative probability reaches `mass`."""
+    normalized = torch.log_softmax(scores, dim=-1)
+    p = torch.exp(normalized)
+    ent = -(normalized * p).nansum(-1, keepdim=True)
+    shifted = torch.abs((-normalized) - ent)
+    sorted_scores, sorted_indices = torch.sort(shifted, descending=False)
+    sorted_logits = scores.gather(-1, sorted_indices)
+    cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+    last_ind = (cum < mass).sum(dim=1).clamp_(min=0)
+    remove_sorted = sorted_scores > sorted_scores.gather(1, last_ind.view(-1, 1))
+    remove = remove_sorted.scatter(1, sorted_indices, remove_sorted)
+    return scores.masked_fill(remove, float("-inf"))
+
+
 def process_logits(logits, input_ids, do_sample=True, repetition_penalty_=2.0, temperature=0.8,
-                   top_k=50, top_p=0.8):
+                   top_k=50, top_p=0.8, typical_mass=None, suppress_token=None):
     """The processor list HF builds for the reference's kwargs: repetition
-    penalty always; temperature/top-k(50, library default)/top-p only when sampling."""
+    penalty always (then SuppressTokens when asked); custom processors (the typical warper of
+    gpt/model.py:536) next; temperature/top-k(50, library default)/top-p only when sampling."""
     s = repetition_penalty(logits.float(), input_ids, repetition_penalty_)
+    if suppress_token is not None:
+        s[:, suppress_token] = float("-inf")
+    if typical_mass:
+        s = typical_filter(s, typical_mass)
     if do_sample:
         s = s / temperature
         s = top_k_filter(s, top_k)
@@ -189,7 +210,7 @@ def process_logits(logits, input_ids, do_sample=True, repetition_penalty_=2.0, t
 
 def generate(W, refer, refer_lengths, text, max_generate_length=600, do_sample=True,
              top_p=0.8, temperature=0.8, repetition_penalty_=2.0, top_k=50, multinomial=None,
-             suppress_eos=False, all_positions=True, return_trace=False):
+             suppress_eos=False, all_positions=True, return_trace=False, typical_mass=None):
     """inference_speech_tortoise (gpt/model.py:514-545) + HF _sample loop.  Returns codes
     [B, G<=max_generate_length] (rows padded with 8193 after EOS).  `multinomial(probs)->[B,1]`
     defaults to torch.multinomial on the global CPU generator (same draw order as HF)."""
@@ -206,9 +227,8 @@ def generate(W, refer, refer_lengths, text, max_generate_length=600, do_sample=T
     while ids.shape[1] < max_length:
         logits, hn = forward_nocache(W, prefix, ids[:, P:], all_positions=all_positions)
         last = logits[:, -1, :].float()
-        s = process_logits(last, ids, do_sample, repetition_penalty_, temperature, top_k, top_p)
-        if suppress_eos:
-            s[:, STOP_MEL] = float("-inf")
+        s = process_logits(last, ids, do_sample, repetition_penalty_, temperature, top_k, top_p, typical_mass,
+                           STOP_MEL if suppress_eos else None)
         if do_sample:
             nxt = multinomial(torch.softmax(s, dim=-1)).squeeze(1)
         else:

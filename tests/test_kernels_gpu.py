@@ -381,12 +381,8 @@ def test_process_logits_and_append(dlib):
     probs = torch.zeros(B, V, device=DEV)
     dlib.call("dtts_process_logits", logits=lg, ldl=V, n_rows=B, vocab=V, ids=idd, ld_ids=64, n_ids=n_ids, penalty=2.0,
               temperature=0.8, top_p=0.8, top_k=50, do_sample=1, suppress_token=8193, probs=probs, ldp=V)
-    s = og.process_logits(logits, ids[:, :n_ids])
-    s[:, 8193] = float("-inf")
-    # suppress happens before top-k in the kernel; redo the oracle in that order
-    s = og.repetition_penalty(logits, ids[:, :n_ids], 2.0)
-    s[:, 8193] = float("-inf")
-    s = og.top_p_filter(og.top_k_filter(s / 0.8, 50), 0.8)
+    # SuppressTokens sits before the sampling warpers in HF's list, i.e. before top-k
+    s = og.process_logits(logits, ids[:, :n_ids], suppress_token=8193)
     ref = torch.softmax(s, -1)
     assert (probs.cpu() - ref).abs().max().item() < 1e-6
     assert torch.equal(probs.cpu() > 0, ref > 0)
@@ -413,6 +409,41 @@ def test_process_logits_and_append(dlib):
     assert int(step) == 4
     assert torch.allclose(x, tok[exp.to(DEV)] + pos[4])
     assert kv_row.tolist() == [b * 200 + 23 for b in range(B)] and kv_len.tolist() == [24] * B
+
+
+def test_process_logits_typical_warper(dlib):
+    """TypicalLogitsWarper on the device (gpt/modules/typical_sampling.py) against the kept sets the unmodified reference
+    produced (tests/golden/make_typical.py) and against the oracle's full chain."""
+    import os
+    import oracle.gpt as og
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "typical.pt"), map_location="cpu")
+    rows = fx["rows"]
+    B, V = rows.shape
+    ids = torch.ones(B, 8, dtype=torch.long)
+    lg, idd = rows.to(DEV).contiguous(), ids.to(DEV)
+    for mass in (0.9, 0.5):
+        kept = fx[f"kept_{mass}"]
+        # the warper alone: penalty 1, temperature 1, top-k 512 (the kernel's maximum), top-p 1
+        probs = torch.zeros(B, V, device=DEV)
+        dlib.call("dtts_process_logits", logits=lg, ldl=V, n_rows=B, vocab=V, ids=idd, ld_ids=8, n_ids=0, penalty=1.0,
+                  temperature=1.0, top_p=1.0, top_k=512, do_sample=1, suppress_token=-1, probs=probs, ldp=V, typical_mass=mass)
+        got = probs.cpu() > 0
+        for b in range(B):
+            if int(kept[b].sum()) <= 512:
+                assert torch.equal(got[b], kept[b]), (mass, b, int(got[b].sum()), int(kept[b].sum()))
+            else:
+                assert int(got[b].sum()) == 512 and bool((got[b] & ~kept[b]).sum() == 0)
+        # the full chain as inference_speech_tortoise(typical_sampling=True) configures it
+        probs.zero_()
+        dlib.call("dtts_process_logits", logits=lg, ldl=V, n_rows=B, vocab=V, ids=idd, ld_ids=8, n_ids=8, penalty=2.0,
+                  temperature=0.8, top_p=0.8, top_k=50, do_sample=1, suppress_token=-1, probs=probs, ldp=V, typical_mass=mass)
+        ref = torch.softmax(og.process_logits(rows, ids, typical_mass=mass), -1)
+        assert torch.equal(probs.cpu() > 0, ref > 0)
+        assert (probs.cpu() - ref).abs().max().item() < 1e-6
+        am = torch.zeros(B, dtype=torch.int64, device=DEV)
+        dlib.call("dtts_process_logits", logits=lg, ldl=V, n_rows=B, vocab=V, ids=idd, ld_ids=8, n_ids=8, penalty=2.0,
+                  temperature=1.0, top_p=1.0, top_k=50, do_sample=0, suppress_token=-1, argmax=am, typical_mass=mass)
+        assert torch.equal(am.cpu(), og.process_logits(rows, ids, do_sample=False, typical_mass=mass).argmax(-1))
 
 
 def test_p_sample_step(dlib):

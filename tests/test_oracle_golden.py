@@ -152,3 +152,16 @@ def test_vqpath_oracle_matches_reference(weights):
         assert recon.shape == fx["recon"][b].shape and wav.shape == fx["wav"][b].shape
         assert (recon - fx["recon"][b]).abs().max() < 1e-5
         assert (wav - fx["wav"][b]).pow(2).mean().sqrt() < 1e-6
+
+
+def test_typical_sampling_oracle_matches_reference(weights):
+    """oracle typical_filter / generate(typical_mass) against the unmodified reference's TypicalLogitsWarper and
+    inference_speech_tortoise(typical_sampling=True) (tests/golden/make_typical.py)."""
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "typical.pt"))
+    for mass in (0.9, 0.5):
+        out = og.typical_filter(fx["rows"].clone(), mass)
+        assert torch.equal(~torch.isinf(out), fx[f"kept_{mass}"])
+    torch.manual_seed(fx["seed"])
+    codes = og.generate(weights, fx["refer"], fx["lengths"], fx["text"], max_generate_length=fx["G"], do_sample=True,
+                        typical_mass=fx["mass"])
+    assert torch.equal(codes, fx["sampled"])

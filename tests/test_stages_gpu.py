@@ -57,6 +57,24 @@ def test_gpt_greedy_and_sampled_tokens(model, golden):
     assert torch.equal(codes_s.cpu(), fx["sampled"]), (codes_s.cpu().tolist(), fx["sampled"].tolist())
 
 
+def test_gpt_typical_sampling_tokens(model):
+    """inference_speech_tortoise(typical_sampling=True) (gpt/model.py:536): sampled and greedy tokens bit-exact against
+    the unmodified reference (tests/golden/make_typical.py)."""
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "typical.pt"), map_location="cpu")
+    text, refer, lens, G = fx["text"], fx["refer"], fx["lengths"].tolist(), fx["G"]
+    torch.manual_seed(fx["seed"])
+    codes = model.gpt.inference_speech_tortoise(refer.to(DEV), lens, text, do_sample=True, top_p=0.8, temperature=0.8,
+                                                num_return_sequences=1, length_penalty=1.0, repetition_penalty=2.0,
+                                                max_generate_length=G, typical_sampling=True, typical_mass=fx["mass"],
+                                                multinomial=CPU_HOOKS["multinomial"])
+    assert torch.equal(codes.cpu(), fx["sampled"]), (codes.cpu().tolist(), fx["sampled"].tolist())
+    codes = model.gpt.inference_speech_tortoise(refer.to(DEV), lens, text, do_sample=False, num_return_sequences=1,
+                                                repetition_penalty=2.0, max_generate_length=G, typical_sampling=True,
+                                                typical_mass=fx["mass"])
+    assert torch.equal(codes.cpu(), fx["greedy"]), (codes.cpu().tolist(), fx["greedy"].tolist())
+
+
 def test_gpt_latents(model, golden):
     fx, lx = golden["gpt"], golden["latent"]
     text, refer, lens = fx["text"], fx["refer"], fx["lengths"].tolist()
