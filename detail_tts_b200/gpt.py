@@ -133,17 +133,19 @@ class _DecodeState:
     recorded launch Plan over these buffers (position / history length come from the device-side `step`), which
     is what makes it capturable into ONE CUDA graph and replayable with no per-token marshalling."""
 
-    def __init__(self, gpt, B, Pmax, G, sampling):
+    def __init__(self, gpt, B, Pmax, G, sampling, n_mel0=1):
+        """n_mel0: mel tokens already in the sequence when decoding starts: 1 (<start_mel>) for
+        inference_speech_tortoise, 2 + len(mel_codes) for inference_speech_valle."""
         do_sample, penalty, temperature, top_p, top_k, suppress_token, typical_mass = sampling
-        self.gpt, self.B, self.G = gpt, B, G
+        self.gpt, self.B, self.G, self.n_mel0 = gpt, B, G, n_mel0
         dev, dt = gpt.device, gpt.dtype
-        self.stride = stride = Pmax + 1 + G                  # KV arena rows per utterance
+        self.stride = stride = Pmax + n_mel0 + G             # KV arena rows per utterance
         self.arena = [torch.zeros(B * stride, 3 * D_MODEL, dtype=dt, device=dev) for _ in range(N_LAYERS)]
-        self.ld_ids = ld_ids = Pmax + 1 + G + 1
+        self.ld_ids = ld_ids = Pmax + n_mel0 + G + 1
         # HF repetition penalty sees the whole row: P fake 1's, 8192, then generated ids.  Rows are right-aligned so
         # that column n_ids0+s is generated token s for every row (extra leading 1's do not change the penalised set).
         self.ids = torch.ones(B, ld_ids, dtype=torch.long, device=dev)
-        self.n_ids0 = n_ids0 = Pmax + 1
+        self.n_ids0 = n_ids0 = Pmax + n_mel0
         e = lambda *shape, d=torch.float32: torch.empty(*shape, dtype=d, device=dev)  # noqa: E731
         self.xs, self.hn, self.t32 = e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL)
         LDL = gpt.mel_head.N if gpt.tf32x3 else VOCAB          # logits row pitch (head padded to a multiple of 4)
@@ -198,7 +200,7 @@ class _DecodeState:
         with lib.record() as self.append_plan:
             lib.call("dtts_append_token", n_rows=B, next=self.nxt, ids=self.ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=self.step,
                      unfinished=self.unfinished, stop_token=STOP_MEL, tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos,
-                     pos=1, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
+                     pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
                      kv_pos_rows=self.kv_base)
         with lib.record() as self.plan:
             if gpt.tf32x3:
@@ -241,14 +243,14 @@ class _DecodeState:
         self.graph = None
         self.eager_runs = 0
 
-    def reset(self, P):
-        """Per-call reset: history ids, finished flags, step counter, per-utterance KV base positions."""
-        dev = self.ids.device
+    def reset(self, P, mel_prefix):
+        """Per-call reset: history ids (fake 1's, then the mel tokens the sequence starts with), finished flags, step
+        counter, per-utterance KV base positions."""
         self.ids.fill_(1)
-        self.ids[:, self.n_ids0 - 1] = START_MEL
+        self.ids[:, self.n_ids0 - self.n_mel0:self.n_ids0] = mel_prefix
         self.unfinished.fill_(1)
         self.step.zero_()
-        self.kv_base.copy_(torch.tensor([p + 1 for p in P], dtype=torch.int32), non_blocking=False)
+        self.kv_base.copy_(torch.tensor([p + self.n_mel0 for p in P], dtype=torch.int32), non_blocking=False)
 
     def _run_plan_pdl(self):
         """The decode step's launches with programmatic dependent launch between them (see dtts_set_pdl)."""
@@ -439,6 +441,33 @@ class UnifiedVoice:
         suppress_tokens=[8193]; `typical_sampling=True` inserts the reference's TypicalLogitsWarper(mass=typical_mass)
         (gpt/modules/typical_sampling.py) after the repetition penalty, where HF puts custom processors.
         `multinomial(probs)->[B,1]` overrides torch.multinomial (tests)."""
+        B = text_inputs.shape[0]
+        start = torch.full((B, 1), START_MEL, dtype=torch.long, device=self.device)
+        return self._sample_codes(speech_conditioning_latent, cond_lengths, text_inputs, start, input_tokens,
+                                  num_return_sequences, max_generate_length, typical_sampling, typical_mass, text_lengths,
+                                  multinomial, sync_every, hf_generate_kwargs)
+
+    def inference_speech_valle(self, speech_conditioning_latent, cond_lengths, text_inputs, mel_codes, input_tokens=None,
+                               num_return_sequences=1, max_generate_length=None, typical_sampling=False, typical_mass=.9,
+                               text_lengths=None, multinomial=None, sync_every=8, **hf_generate_kwargs):
+        """gpt/model.py:546-579: continue a given mel-code prompt `mel_codes` [B, n].  The reference's `fake_inputs`
+        holds one more placeholder than the cached prefix is long, so the decoded sequence starts with the mel tokens
+        [1, <start_mel>, mel_codes...] (`input_ids[:, mel_len:]`, gpt/model.py:133-135) -- kept as is, including the
+        repetition penalty over them.  Returns only the newly generated codes, like the reference."""
+        B = text_inputs.shape[0]
+        dev = self.device
+        mel_codes = mel_codes.to(dev, torch.long).reshape(B, -1)
+        prefix = torch.cat([torch.ones(B, 1, dtype=torch.long, device=dev),
+                            torch.full((B, 1), START_MEL, dtype=torch.long, device=dev), mel_codes], 1)
+        return self._sample_codes(speech_conditioning_latent, cond_lengths, text_inputs, prefix, input_tokens,
+                                  num_return_sequences, max_generate_length, typical_sampling, typical_mass, text_lengths,
+                                  multinomial, sync_every, hf_generate_kwargs)
+
+    def _sample_codes(self, speech_conditioning_latent, cond_lengths, text_inputs, mel_prefix, input_tokens,
+                      num_return_sequences, max_generate_length, typical_sampling, typical_mass, text_lengths, multinomial,
+                      sync_every, hf_generate_kwargs):
+        """KV-cached HF-style sampling shared by the two entry points; `mel_prefix` [B, n_mel0] are the mel tokens the
+        sequence starts with (their embeddings go through the prefill, their ids into the repetition-penalty set)."""
         assert input_tokens is None and num_return_sequences == 1, \
             "input_tokens / num_return_sequences > 1 are not implemented"
         kw = dict(hf_generate_kwargs)
@@ -458,16 +487,16 @@ class UnifiedVoice:
         dev = self.device
         B = text_inputs.shape[0]
         tl = self._text_lengths(text_inputs, text_lengths)
-        G = int(max_generate_length) if max_generate_length is not None else self.max_mel_positions - 3
-        assert 1 <= G <= self.max_mel_positions - 2
+        n_mel0 = mel_prefix.shape[1]
+        G = int(max_generate_length) if max_generate_length is not None else self.max_mel_positions - 2 - n_mel0
+        assert 1 <= G <= self.max_mel_positions - 1 - n_mel0, "mel position table too short for prompt + generation"
 
         cond = self.get_conditioning(speech_conditioning_latent.to(dev), cond_lengths)
-        start = torch.full((B, 1), START_MEL, dtype=torch.long, device=dev)
-        x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, start, [1] * B)
+        x, seq_off, seq_len, P = self._build_sequences(cond, text_inputs, tl, mel_prefix, [n_mel0] * B)
         Pmax = max(P)
         st = self._decode_state(B, Pmax, G, (do_sample, penalty, temperature, top_p, top_k, suppress_token,
-                                             float(typical_mass) if typical_sampling else 0.0))
-        st.reset(P)
+                                             float(typical_mass) if typical_sampling else 0.0), n_mel0)
+        st.reset(P, mel_prefix)
         y = self._trunk_rows(x, seq_off, seq_len, st.arena, st.stride)
 
         # first token: from the prefill's last position (the <start_mel> token) of every utterance
@@ -503,16 +532,16 @@ class UnifiedVoice:
         self.last_plan = st.plan
         return codes
 
-    def _decode_state(self, B, Pmax, G, sampling):
+    def _decode_state(self, B, Pmax, G, sampling, n_mel0=1):
         """Persistent decode workspace (KV arena, step buffers, recorded launch plans, captured CUDA graph) for one
         (batch, prefix capacity, generation cap, sampling config): reused across calls, so the per-call cost is a
         few small resets instead of re-recording / re-capturing ~95 launches."""
-        key = (B, Pmax, G, sampling)
+        key = (B, Pmax, G, sampling, n_mel0)
         st = self._states.get(key)
         if st is None:
             if len(self._states) >= 4:
                 self._states.clear()
-            st = self._states[key] = _DecodeState(self, B, Pmax, G, sampling)
+            st = self._states[key] = _DecodeState(self, B, Pmax, G, sampling, n_mel0)
         return st
 
     inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528

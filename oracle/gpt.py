@@ -210,20 +210,25 @@ def process_logits(logits, input_ids, do_sample=True, repetition_penalty_=2.0, t
 
 def generate(W, refer, refer_lengths, text, max_generate_length=600, do_sample=True,
              top_p=0.8, temperature=0.8, repetition_penalty_=2.0, top_k=50, multinomial=None,
-             suppress_eos=False, all_positions=True, return_trace=False, typical_mass=None):
+             suppress_eos=False, all_positions=True, return_trace=False, typical_mass=None, mel_codes=None):
     """inference_speech_tortoise (gpt/model.py:514-545) + HF _sample loop.  Returns codes
     [B, G<=max_generate_length] (rows padded with 8193 after EOS).  `multinomial(probs)->[B,1]`
-    defaults to torch.multinomial on the global CPU generator (same draw order as HF)."""
+    defaults to torch.multinomial on the global CPU generator (same draw order as HF).
+    `mel_codes` [B,n]: inference_speech_valle (gpt/model.py:546-579) -- the reference's fake_inputs then holds one
+    placeholder more than the cached prefix is long, so the mel part of the sequence starts [1, <start>, mel_codes]."""
     if multinomial is None:
         multinomial = lambda p: torch.multinomial(p, num_samples=1)  # noqa: E731
     prefix = prefix_embeddings(W, refer, refer_lengths, text)
     B, P, _ = prefix.shape
-    fake = torch.ones(B, P + 1, dtype=torch.long)
-    fake[:, -1] = START_MEL
-    ids = fake
+    if mel_codes is None:
+        mel0 = torch.full((B, 1), START_MEL, dtype=torch.long)
+    else:
+        mel0 = torch.cat([torch.ones(B, 1, dtype=torch.long), torch.full((B, 1), START_MEL, dtype=torch.long),
+                          mel_codes.long()], 1)
+    ids = torch.cat([torch.ones(B, P, dtype=torch.long), mel0], 1)
     unfinished = torch.ones(B, dtype=torch.long)
     trace = []
-    max_length = P + 1 + max_generate_length
+    max_length = ids.shape[1] + max_generate_length
     while ids.shape[1] < max_length:
         logits, hn = forward_nocache(W, prefix, ids[:, P:], all_positions=all_positions)
         last = logits[:, -1, :].float()
@@ -240,7 +245,7 @@ def generate(W, refer, refer_lengths, text, max_generate_length=600, do_sample=T
         unfinished = unfinished & (nxt != STOP_MEL).long()
         if unfinished.max() == 0:
             break
-    codes = ids[:, P + 1:]
+    codes = ids[:, P + mel0.shape[1]:]
     return (codes, trace) if return_trace else codes
 
 

@@ -165,3 +165,11 @@ def test_typical_sampling_oracle_matches_reference(weights):
     codes = og.generate(weights, fx["refer"], fx["lengths"], fx["text"], max_generate_length=fx["G"], do_sample=True,
                         typical_mass=fx["mass"])
     assert torch.equal(codes, fx["sampled"])
+
+
+def test_valle_oracle_matches_reference(weights):
+    """oracle generate(mel_codes=...) against the unmodified reference's inference_speech_valle (tests/golden/make_valle.py)."""
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "valle.pt"))
+    codes = og.generate(weights, fx["refer"], fx["lengths"], fx["text"], max_generate_length=fx["G"], do_sample=False,
+                        mel_codes=fx["mel_codes"])
+    assert torch.equal(codes, fx["greedy"])

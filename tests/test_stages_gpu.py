@@ -75,6 +75,26 @@ def test_gpt_typical_sampling_tokens(model):
     assert torch.equal(codes.cpu(), fx["greedy"]), (codes.cpu().tolist(), fx["greedy"].tolist())
 
 
+def test_gpt_valle_prompted_tokens(model):
+    """inference_speech_valle (gpt/model.py:546-579): continuing a mel-code prompt, sampled and greedy tokens bit-exact
+    against the unmodified reference (tests/golden/make_valle.py)."""
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "valle.pt"), map_location="cpu")
+    text, refer, lens, G, mc = fx["text"], fx["refer"], fx["lengths"].tolist(), fx["G"], fx["mel_codes"]
+    torch.manual_seed(fx["seed"])
+    codes = model.gpt.inference_speech_valle(refer.to(DEV), lens, text, mc, do_sample=True, top_p=0.8, temperature=0.8,
+                                             num_return_sequences=1, length_penalty=1.0, repetition_penalty=2.0,
+                                             max_generate_length=G, multinomial=CPU_HOOKS["multinomial"])
+    assert torch.equal(codes.cpu(), fx["sampled"]), (codes.cpu().tolist(), fx["sampled"].tolist())
+    codes = model.gpt.inference_speech_valle(refer.to(DEV), lens, text, mc, do_sample=False, num_return_sequences=1,
+                                             repetition_penalty=2.0, max_generate_length=G)
+    assert torch.equal(codes.cpu(), fx["greedy"]), (codes.cpu().tolist(), fx["greedy"].tolist())
+    # the tortoise entry point still works on the same decode-state cache afterwards
+    c2 = model.gpt.inference_speech_tortoise(refer.to(DEV), lens, text, do_sample=False, num_return_sequences=1,
+                                             repetition_penalty=2.0, max_generate_length=4)
+    assert c2.shape == (2, 4)
+
+
 def test_gpt_latents(model, golden):
     fx, lx = golden["gpt"], golden["latent"]
     text, refer, lens = fx["text"], fx["refer"], fx["lengths"].tolist()
