@@ -412,6 +412,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_mean_rows_params); SZ(dtts_tsemb_params); SZ(dtts_couple_params); SZ(dtts_zp_params);
   SZ(dtts_rowutt_params); SZ(dtts_copy_utts_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
   SZ(dtts_voc_mrf_params); SZ(dtts_conv_post_params); SZ(dtts_stft_frames_params); SZ(dtts_spec_mag_params);
-  SZ(dtts_gn_apply_params); SZ(dtts_zero_params);
+  SZ(dtts_gn_apply_params); SZ(dtts_zero_params); SZ(dtts_gpt_step_params);
   return -1;
 }

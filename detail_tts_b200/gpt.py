@@ -26,6 +26,10 @@ N_LAYERS, N_HEADS, D_MODEL, HEAD_DIM = 10, 16, 768, 48
 VOCAB = 8194
 # decode step: the split-K reduce of the QKV GEMM runs inside the attention kernel (one launch less per layer)
 FUSE_QKV_REDUCE = os.environ.get("DTTS_FUSE_QKV", "1") != "0"
+# decode step for small batches (<= MEGA_MAX_B utterances) as one persistent cooperative kernel (csrc/gpt_mega.cu).
+# Measured per step as one CUDA graph (B200): B=1 0.45 ms vs 0.64 ms kernel by kernel, B=4 0.47 vs 0.61; B=16 0.65 vs 0.63;
+# B=32 0.98 vs 0.66 -- the ~52 grid barriers cost ~3.5 us each and the per-row work grows faster than on the tensor cores.
+MEGA_MAX_B = int(os.environ.get("DTTS_GPT_MEGA_MAX_B", "4"))
 
 
 def _i32(x, device):
@@ -202,8 +206,30 @@ class _DecodeState:
                      unfinished=self.unfinished, stop_token=STOP_MEL, tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos,
                      pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
                      kv_pos_rows=self.kv_base)
+        self.mega = gpt.tf32x3 and B <= min(MEGA_MAX_B, 32)
         with lib.record() as self.plan:
-            if gpt.tf32x3:
+            if self.mega:
+                # one persistent kernel for the whole step (fp32 weights = hi + lo of the 3xTF32 packing, exact)
+                mw = gpt.mega_weights()
+                table = []
+                for l, lw in enumerate(mw["layers"]):
+                    table += [t.data_ptr() for t in lw] + [arena[l].data_ptr()]
+                self.layer_ptrs = torch.tensor(table, dtype=torch.int64, device=dev)
+                self.mega_scratch = [e(B, D_MODEL), e(B, D_MODEL), e(B, D_MODEL), e(B, 4 * D_MODEL), e(2, B, D_MODEL)]
+                self.barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+                xa, xb, att, uu, part = self.mega_scratch
+                lib.call("dtts_gpt_decode_step", B=B, n_layers=N_LAYERS, d_model=D_MODEL, n_heads=N_HEADS, d_ff=4 * D_MODEL,
+                         layer_ptrs=self.layer_ptrs, lnf_g=T.ln_f[0], lnf_b=T.ln_f[1], fn_g=gpt.final_norm[0],
+                         fn_b=gpt.final_norm[1], w_head=mw["head_w"], b_head=mw["head_b"], vocab=VOCAB, ld_logits=LDL,
+                         x_in=xs, xa=xa, xb=xb, att=att, u=uu, part=part, hn=hn, logits=self.logits, kv_row=kv_row,
+                         k_off=k_off, kv_len=kv_len, arena_ld=3 * D_MODEL, max_k_len=stride, barrier=self.barrier,
+                         ln_eps=1e-5)
+                self.plan.keep.extend(t for lw in mw["layers"] for t in lw)
+                lib.call("dtts_process_logits", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
+                         n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                         do_sample=int(do_sample), suppress_token=suppress_token, probs=self.probs, ldp=VOCAB,
+                         argmax=self.argmax, typical_mass=typical_mass)
+            elif gpt.tf32x3:
                 ops.splitk_reduce(None, 0, B, D_MODEL, res=xs, ln=T.layers[0]["ln1"], y_hi=xh, y_lo=xl)
                 for l, ly in enumerate(T.layers):
                     ops.gemm_tf32x3(xh, xl, ly["attn"], wsv["attn"], split_k=S["attn"])
@@ -239,7 +265,8 @@ class _DecodeState:
                     ops.gemm(hdt, ly["fc"], act=ops.ACT_GELU_NEW, **_o(udt))
                     ops.gemm(udt, ly["out"], res=xs, out32=xs)
                 ops.layernorm(xs, *T.ln_f, out32=t32)
-            head()
+            if not self.mega:
+                head()
         self.graph = None
         self.eager_runs = 0
 
@@ -309,8 +336,23 @@ class UnifiedVoice:
         self.use_cuda_graph = True      # replay the ~95-launch decode step as one CUDA graph
         self.use_pdl = os.environ.get("DTTS_PDL", "0") != "0"   # programmatic dependent launch between the step's kernels (measured: no gain, 1185 vs 1132 us)
         self._states = {}
+        self._mega_w = None
 
     # ------------------------------------------------------------------------------------------
+    def mega_weights(self):
+        """Plain fp32 [N, K] weights for the persistent small-batch decode kernel: hi + lo of the 3xTF32 packing is the
+        original fp32 weight exactly (pack.split_tf32_host).  Built on first use (+308 MB of HBM)."""
+        if self._mega_w is None:
+            assert self.tf32x3
+            full = lambda pw: (pw.w + pw.w_lo).contiguous()  # noqa: E731
+            layers = []
+            for ly in self.trunk.layers:
+                layers.append([ly["ln1"][0], ly["ln1"][1], full(ly["attn"]), ly["attn"].bias, full(ly["proj"]), ly["proj"].bias,
+                               ly["ln2"][0], ly["ln2"][1], full(ly["fc"]), ly["fc"].bias, full(ly["out"]), ly["out"].bias])
+            self._mega_w = dict(layers=layers, head_w=full(self.mel_head)[:VOCAB].contiguous(),
+                                head_b=self.mel_head.bias[:VOCAB].contiguous())
+        return self._mega_w
+
     def _o(self, t):
         return {"out16": t} if self.dtype == torch.float16 else {"out32": t}
 

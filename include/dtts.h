@@ -182,6 +182,33 @@ typedef struct {
  * gpt/modules/typical_sampling.py:5-33 (custom processors run after the penalty and before the sampling warpers). */
 int dtts_process_logits(const dtts_logits_params* p, void* stream);
 
+/* The whole KV-cached decode step of the GPT for a SMALL batch (B <= 32) as one persistent cooperative kernel: per layer
+ * ln_1 -> c_attn -> attention over the KV arena -> c_proj + residual -> ln_2 -> c_fc -> gelu_new -> c_proj + residual, then
+ * ln_f -> final_norm (latent) -> mel_head logits (gpt/model.py:107-185,392-417 + HF modeling_gpt2.py:229-310).  Exact fp32
+ * FMA arithmetic; phases are separated by a grid barrier instead of ~84 launch boundaries.  Weights are plain fp32
+ * [N, K] row-major (nn.Linear layout; HF Conv1D transposed). */
+enum { DTTS_GPT_LAYER_PTRS = 13 };
+typedef struct {
+  int B, n_layers, d_model, n_heads, d_ff;
+  /* device table [n_layers][DTTS_GPT_LAYER_PTRS] of device addresses, per layer in this order:
+   * ln1_g ln1_b w_qkv[2304,768] b_qkv w_proj[768,768] b_proj ln2_g ln2_b w_fc[3072,768] b_fc w_out[768,3072] b_out arena */
+  const uint64_t* layer_ptrs;
+  const float* lnf_g; const float* lnf_b; const float* fn_g; const float* fn_b;     /* ln_f, final_norm */
+  const float* w_head; const float* b_head; int vocab; int ld_logits;                /* mel_head [vocab, 768] */
+  const float* x_in;            /* [B, 768] embedding of the current token (dtts_append_token output) */
+  float* xa; float* xb;         /* [B, 768] scratch: residual stream ping-pong */
+  float* att; float* u;         /* [B, 768], [B, 3072] scratch */
+  float* part;                  /* [2, B, 768] scratch: split-K partials */
+  float* hn;                    /* optional [B, 768]: final_norm output = the diffusion latent of this position */
+  float* logits;                /* [B, ld_logits] */
+  const int* kv_row;            /* [B] arena row of the new token */
+  const int* k_off; const int* kv_len;   /* [B] first arena row / number of visible positions (incl. the new one) of utterance b */
+  int arena_ld, max_k_len;      /* arena row pitch (>= 2304: q | k | v); bound on kv_len (shared-memory score buffer) */
+  uint32_t* barrier;            /* [2], zero-initialised once by the caller: grid-barrier state */
+  float ln_eps;
+} dtts_gpt_step_params;
+int dtts_gpt_decode_step(const dtts_gpt_step_params* p, void* stream);
+
 typedef struct {
   int n_rows;
   const int64_t* next; int64_t* ids; int ld_ids; int n_ids;  /* ids[:, n_ids] = next (or stop if finished) */

@@ -44,7 +44,18 @@ def test_mel_style_encoder(model, golden, weights):
     assert relrms(out2[1], o2[0, :, 0]) < 3e-3
 
 
-def test_gpt_greedy_and_sampled_tokens(model, golden):
+@pytest.fixture(params=["persistent_step", "kernel_by_kernel_step"])
+def step_mode(request, model, monkeypatch):
+    """Both implementations of the decode step: the persistent cooperative kernel (batches <= 32, csrc/gpt_mega.cu) and
+    the kernel-by-kernel 3xTF32 step (the large-batch path), each with its own cached decode state."""
+    import detail_tts_b200.gpt as G
+    monkeypatch.setattr(G, "MEGA_MAX_B", 32 if request.param == "persistent_step" else 0)
+    model.gpt._states.clear()
+    yield request.param
+    model.gpt._states.clear()
+
+
+def test_gpt_greedy_and_sampled_tokens(model, golden, step_mode):
     fx = golden["gpt"]
     text, refer, lens, G = fx["text"], fx["refer"], fx["lengths"].tolist(), fx["G"]
     codes = model.gpt.inference_speech_tortoise(refer.to(DEV), lens, text, do_sample=False, num_return_sequences=1,
@@ -55,6 +66,26 @@ def test_gpt_greedy_and_sampled_tokens(model, golden):
                                                   num_return_sequences=1, length_penalty=1.0, repetition_penalty=2.0,
                                                   max_generate_length=G, multinomial=CPU_HOOKS["multinomial"])
     assert torch.equal(codes_s.cpu(), fx["sampled"]), (codes_s.cpu().tolist(), fx["sampled"].tolist())
+
+
+def test_gpt_persistent_step_wide_batch(model, golden, monkeypatch):
+    """The 32-row variant of the persistent decode kernel (17..32 utterances): greedy tokens of a 20-utterance batch
+    (the fixture's two utterances repeated) equal the reference's, and the captured latents agree with the kernel-by-kernel
+    step."""
+    import detail_tts_b200.gpt as G
+    fx = golden["gpt"]
+    rep = 10
+    text, refer, lens = fx["text"].repeat(rep, 1), fx["refer"].repeat(rep, 1, 1), fx["lengths"].tolist() * rep
+    lat = {}
+    for mode, cap in (("persistent", 32), ("kernel_by_kernel", 0)):
+        monkeypatch.setattr(G, "MEGA_MAX_B", cap)
+        model.gpt._states.clear()
+        codes = model.gpt.inference_speech_tortoise(refer.to(DEV), lens, text, do_sample=False, num_return_sequences=1,
+                                                    repetition_penalty=2.0, max_generate_length=fx["G"])
+        assert torch.equal(codes.cpu(), fx["greedy"].repeat(rep, 1)), mode
+        lat[mode] = model.gpt.last_latents[:, :codes.shape[1]].clone()
+    model.gpt._states.clear()
+    assert relrms(lat["persistent"], lat["kernel_by_kernel"].cpu()) < 1e-5
 
 
 def test_gpt_typical_sampling_tokens(model):
@@ -95,7 +126,7 @@ def test_gpt_valle_prompted_tokens(model):
     assert c2.shape == (2, 4)
 
 
-def test_gpt_latents(model, golden):
+def test_gpt_latents(model, golden, step_mode):
     fx, lx = golden["gpt"], golden["latent"]
     text, refer, lens = fx["text"], fx["refer"], fx["lengths"].tolist()
     codes = lx["codes"]
