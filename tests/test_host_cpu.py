@@ -32,6 +32,18 @@ def test_abi_symbols_and_struct_sizes():
     assert L.launches() == 0
 
 
+def test_integration_md_ctypes_stub_matches_library():
+    """The hand-written ctypes struct INTEGRATION.md shows to a reference maintainer has the library's layout."""
+    import ctypes
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    a = src.index("class GemmParams(ctypes.Structure):")
+    b = src.index('assert lib.dtts_sizeof(b"dtts_gemm_params")')
+    ns = {}
+    exec("import ctypes\n" + src[a:b], ns)
+    lib = ctypes.CDLL(os.path.join(ROOT, "detail_tts_b200", "libdtts.so"))
+    assert lib.dtts_sizeof(b"dtts_gemm_params") == ctypes.sizeof(ns["GemmParams"])
+
+
 def test_product_path_has_no_cpu_fallback():
     from detail_tts_b200.model import SynthesizerTrn
     if torch.cuda.is_available():
