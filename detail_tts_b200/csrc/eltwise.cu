@@ -233,9 +233,11 @@ stft_frames_kernel(const dtts_stft_frames_params p) {
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int r = (int)(idx / p.n_fft), k = (int)(idx - (long)r * p.n_fft);
     int i = r * p.hop + k - p.pad;
-    if (i < 0) i = -i;                       // reflect (no edge repeat), torch F.pad(mode="reflect")
-    if (i >= n) i = 2 * (n - 1) - i;
-    const float v = (i >= 0 && i < n) ? w[i] * __ldg(p.window + k) : 0.f;
+    if (!p.zero_pad) {
+      if (i < 0) i = -i;                     // reflect (no edge repeat), torch F.pad(mode="reflect")
+      if (i >= n) i = 2 * (n - 1) - i;
+    }
+    const float v = (i >= 0 && i < n) ? (p.window ? w[i] * __ldg(p.window + k) : w[i]) : 0.f;
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     p.out_hi[(row0 + r) * p.ld + k] = hi;
     p.out_lo[(row0 + r) * p.ld + k] = v - hi;
@@ -383,7 +385,7 @@ extern "C" int dtts_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 #define SZ(name) if (!strcmp(struct_name, #name)) return (int)sizeof(name)
 extern "C" int dtts_stft_frames(const dtts_stft_frames_params* p, void* stream) {
-  DTTS_REQUIRE(p && p->wav && p->wav_len && p->utt_off && p->utt_len && p->window && p->out_hi && p->out_lo, "stft_frames: null argument");
+  DTTS_REQUIRE(p && p->wav && p->wav_len && p->utt_off && p->utt_len && (p->window || p->zero_pad) && p->out_hi && p->out_lo, "stft_frames: null argument");
   DTTS_REQUIRE(p->n_fft > 0 && p->hop > 0 && p->pad >= 0 && p->ld >= p->n_fft, "stft_frames: bad shape");
   if (p->n_utt <= 0 || p->max_frames <= 0) return 0;
   long g = ((long)p->max_frames * p->n_fft + 255) / 256;

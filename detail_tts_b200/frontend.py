@@ -94,6 +94,67 @@ class MelFrontEnd:
         return out, frames
 
 
+def sinc_resample_kernel(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """The windowed-sinc polyphase filter bank of torchaudio.functional.resample (`sinc_interp_hann`, the defaults
+    torchaudio.transforms.Resample uses at api.py:37), restated from its definition in float64:
+    kernel[j, k] = sinc(t) * cos^2(t*pi/(2*lpw)) * base/orig with t = clamp((-j/new + (k - width)/orig) * base, +-lpw).
+    Returns (kernel [new, 2*width+orig] fp32, width, orig, new) for the reduced ratio orig/new."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = int(math.ceil(lowpass_filter_width * orig / base))
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    t = (np.arange(0, -new, -1, dtype=np.float64)[:, None] / new + idx) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * np.pi / lowpass_filter_width / 2) ** 2
+    t = t * np.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t) * window * (base / orig)
+    return k.astype(np.float32), width, orig, new
+
+
+class Resample:
+    """torchaudio.transforms.Resample(orig_freq, new_freq) (api.py:37) on the GPU: zero-padded framing (dtts_stft_frames,
+    frame f = samples [f*orig - width, f*orig + width + orig)) x the [new, 2*width+orig] sinc kernel as one 3xTF32
+    tensor-core GEMM (fp32-class); row f of the result holds output samples f*new .. f*new+new-1."""
+
+    def __init__(self, orig_freq, new_freq, device="cuda", lowpass_filter_width=6, rolloff=0.99):
+        self.device = torch.device(device)
+        k, self.width, self.orig, self.new = sinc_resample_kernel(orig_freq, new_freq, lowpass_filter_width, rolloff)
+        self.klen = k.shape[1]
+        self.kp = (self.klen + 3) // 4 * 4
+        kpad = torch.zeros(self.new, self.kp)
+        kpad[:, :self.klen] = torch.from_numpy(k)
+        self.kernel = pack.pack_linear_tf32x3(kpad, None, self.device, n_pad=4)
+
+    @torch.no_grad()
+    def __call__(self, waveform, lengths=None):
+        """waveform [B, L] (or [L]) fp32 -> [B, ceil(new*L/orig)]; `lengths`: valid samples per row (ragged batch: every
+        row is resampled as if alone; the tail beyond its own target length is zero)."""
+        if self.orig == self.new:
+            return waveform
+        dev = self.device
+        squeeze = waveform.dim() == 1
+        y = waveform.reshape(-1, waveform.shape[-1]).to(dev, torch.float32).contiguous()
+        B, L = y.shape
+        lens = [L] * B if lengths is None else [int(v) for v in lengths]
+        frames = [n // self.orig + 1 for n in lens]                   # conv1d(stride=orig) over the padded signal
+        target = [-(-self.new * n // self.orig) for n in lens]        # ceil(new * L / orig)
+        lay = RowsLayout(frames, 0, dev)
+        fh = torch.zeros(lay.M, self.kp, device=dev)
+        fl = torch.zeros(lay.M, self.kp, device=dev)
+        ops._lib.lib().call("dtts_stft_frames", wav=y, ldw=L, wav_len=torch.tensor(lens, dtype=torch.int32, device=dev), n_utt=B,
+                            utt_off=lay.off, utt_len=lay.len, max_frames=max(frames), n_fft=self.klen, hop=self.orig,
+                            pad=self.width, window=None, out_hi=fh, out_lo=fl, ld=self.kp, zero_pad=1)
+        res = torch.empty(lay.M, self.kernel.N, device=dev)
+        ops.gemm_tf32x3(fh, fl, self.kernel, res, bias=False)
+        out = torch.zeros(B, max(target), device=dev)
+        for b in range(B):
+            o, f = lay.offs[b], frames[b]
+            out[b, :target[b]] = res[o:o + f, :self.new].reshape(-1)[:target[b]]
+        return out[0] if squeeze else out
+
+
 _CACHE = {}
 
 

@@ -268,11 +268,14 @@ typedef struct {
   int n_utt; const int* utt_off; const int* utt_len;   /* frame rows of utterance b: (wav_len + 2*pad - n_fft)/hop + 1 */
   int max_frames;
   int n_fft, hop, pad;          /* 1024, 256, (n_fft - hop)/2 = 384: reflect padding at both ends, center=False */
-  const float* window;          /* [n_fft] periodic Hann (torch.hann_window) */
+  const float* window;          /* [n_fft] periodic Hann (torch.hann_window); NULL = rectangular */
   float* out_hi; float* out_lo; int ld;   /* [M, n_fft] windowed frames split x = hi + lo (hi tf32-exact) */
+  int zero_pad;                 /* 0: reflect padding (STFT); 1: zeros outside the waveform (polyphase resampler framing) */
 } dtts_stft_frames_params;
 /* Framing + windowing of mel_spectrogram_torch (vqvae/utils/data_utils.py:120-141: F.pad reflect + torch.stft framing).
- * The DFT itself is dtts_gemm_tf32x3 against a [cos | -sin] basis (fp32-class). */
+ * The DFT itself is dtts_gemm_tf32x3 against a [cos | -sin] basis (fp32-class).  With zero_pad = 1 and no window the same
+ * kernel frames the input of the sinc resampler api.py:37 applies to the prompt (torchaudio.transforms.Resample): frame
+ * f = samples [f*orig - width, f*orig + width + orig), which dtts_gemm_tf32x3 multiplies with the [new, 2*width+orig] kernel. */
 int dtts_stft_frames(const dtts_stft_frames_params* p, void* stream);
 
 typedef struct {

@@ -42,3 +42,27 @@ def mel_spectrogram(y, n_fft=1024, num_mels=128, sampling_rate=24000, hop_size=2
     spec = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-6)
     mel = torch.matmul(mel_basis(sampling_rate, n_fft, num_mels, fmin, fmax), spec)
     return torch.log(torch.clamp(mel, min=1e-5))
+
+
+def resample(y, orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """torchaudio.transforms.Resample(orig_freq, new_freq)(y) as api.py:37 applies it to the prompt (torchaudio
+    functional.resample, method sinc_interp_hann), restated: float64 windowed-sinc kernel [new, 1, 2*width+orig],
+    zero padding (width, width+orig), conv1d with stride orig, interleave, trim to ceil(new*L/orig).  y [B, L] fp32."""
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    if orig == new:
+        return y
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float64)[:, None, None] / new + idx
+    t = (t * base).clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    kernel = (torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t) * window * (base / orig)).float()
+    L = y.shape[-1]
+    x = torch.nn.functional.pad(y.float(), (width, width + orig))
+    out = torch.nn.functional.conv1d(x[:, None], kernel, stride=orig)          # [B, new, frames]
+    out = out.transpose(1, 2).reshape(y.shape[0], -1)
+    return out[:, :math.ceil(new * L / orig)]

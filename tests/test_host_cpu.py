@@ -281,3 +281,17 @@ def test_slaney_filterbank_matches_oracle():
     assert a.shape == b.shape == (128, 513)
     assert float((a - b).abs().max()) < 1e-7
     assert float(a.sum(1).min()) > 0        # every filter has support at n_fft = 1024
+
+
+def test_sinc_resample_kernel_matches_oracle_definition():
+    """frontend.sinc_resample_kernel (numpy, float64) == the kernel the oracle builds with torch for 44.1 kHz -> 24 kHz."""
+    from detail_tts_b200.frontend import sinc_resample_kernel
+    k, width, orig, new = sinc_resample_kernel(44100, 24000)
+    assert (orig, new, width) == (147, 80, 12) and k.shape == (80, 171)
+    import math
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None] / orig
+    t = (torch.arange(0, -new, -1, dtype=torch.float64)[:, None] / new + idx) * (80 * 0.99)
+    t = t.clamp(-6, 6)
+    ref = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), (t * math.pi).sin() / (t * math.pi)) \
+        * torch.cos(t * math.pi / 12) ** 2 * (80 * 0.99 / 147)
+    assert (torch.from_numpy(k).double() - ref).abs().max() < 1e-7

@@ -173,3 +173,13 @@ def test_valle_oracle_matches_reference(weights):
     codes = og.generate(weights, fx["refer"], fx["lengths"], fx["text"], max_generate_length=fx["G"], do_sample=False,
                         mel_codes=fx["mel_codes"])
     assert torch.equal(codes, fx["greedy"])
+
+
+def test_resample_oracle_matches_torchaudio():
+    """oracle resample against torchaudio.transforms.Resample(sr, 24000) outputs (api.py:37; tests/golden/make_resample.py)."""
+    import oracle.frontend as ofe
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resample.pt"))
+    for name, it in fx.items():
+        out = ofe.resample(it["wav"], it["sr"], 24000)
+        assert out.shape == it["out"].shape, name
+        assert (out - it["out"]).abs().max() < 1e-5, name

@@ -402,3 +402,24 @@ def test_infer_gpt_end_to_end_matches_oracle(model, weights):
     e = rms(wav, owav)
     print("infer_gpt e2e wav rms err", e)
     assert e < 1e-4, e
+
+
+def test_frontend_resample_matches_torchaudio(dlib):
+    """The prompt resampler (api.py:37) on the GPU against torchaudio's outputs (tests/golden/make_resample.py), and the
+    ragged-batch form against per-row calls."""
+    import os
+    from detail_tts_b200.frontend import Resample
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resample.pt"), map_location="cpu")
+    for name, it in fx.items():
+        rs = Resample(it["sr"], 24000, device=DEV)
+        out = rs(it["wav"])
+        assert out.shape == it["out"].shape, (name, out.shape, it["out"].shape)
+        e = (out.cpu() - it["out"]).abs().max().item()
+        print(name, "resample max abs err", e)
+        assert e < 2e-5, (name, e)
+    it = fx["synthetic_44100"]
+    rs = Resample(44100, 24000, device=DEV)
+    lens = [22050, 15001]
+    out = rs(it["wav"], lengths=lens)
+    one = rs(it["wav"][1:2, :15001])
+    assert torch.equal(out[1, :one.shape[1]], one[0]) and out[1, one.shape[1]:].abs().max().item() == 0
