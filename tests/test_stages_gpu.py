@@ -423,3 +423,22 @@ def test_frontend_resample_matches_torchaudio(dlib):
     out = rs(it["wav"], lengths=lens)
     one = rs(it["wav"][1:2, :15001])
     assert torch.equal(out[1, :one.shape[1]], one[0]) and out[1, one.shape[1]:].abs().max().item() == 0
+
+
+def test_api_prompt_from_wav_and_synthesize(model):
+    """api.py:34-49 end to end: 44.1 kHz prompt -> resample -> log-mel on the GPU against the oracle chain, then one
+    synthesis call through the api.py-shaped helper."""
+    import os
+    import oracle.frontend as ofe
+    from detail_tts_b200 import api
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resample.pt"), map_location="cpu")["prompt_1wav"]
+    spec, sl = api.prompt_from_wav(fx["wav"], fx["sr"], device=DEV)
+    ref = ofe.mel_spectrogram(ofe.resample(fx["wav"], fx["sr"], 24000))
+    assert spec.shape == ref.shape and int(sl[0]) == ref.shape[-1]
+    e = (spec.cpu() - ref).abs().max().item()
+    print("prompt log-mel max abs err", e)
+    assert e < 2e-3, e
+    g = torch.Generator().manual_seed(5)
+    toks = torch.randint(3, 255, (1, 9), generator=g)
+    wav = api.synthesize(model, toks, fx["wav"], fx["sr"], max_generate_length=4, suppress_eos=True)
+    assert wav.shape == (1, 1, 3 * 1024) and bool(torch.isfinite(wav).all()) and float(wav.abs().max()) > 0
