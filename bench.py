@@ -175,7 +175,7 @@ def gemm_roofline(model, lib, pk):
     # DRAM bytes per launch of the same 62 launches from the committed ncu capture (never measured live under a profiler)
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_E_gemm_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_G_gemm_traffic.json")))
         if tj["launches"] == len(ms):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:

@@ -63,13 +63,20 @@ class Plan:
         self.lib = lib
         self.calls = []      # (cfunc, struct)
         self.keep = []       # tensors kept alive
+        self.n_kernels = 0
 
     def run(self, stream=None):
         st = ctypes.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        n0 = self.lib.cdll.dtts_kernel_launches()
         for fn, s in self.calls:
             rc = fn(ctypes.byref(s), st)
             if rc != 0:
                 raise DttsError(f"{fn.__name__} failed ({rc}): {self.lib.last_error()}")
+        self.n_kernels = self.lib.cdll.dtts_kernel_launches() - n0     # kernels one run (or one graph replay) launches
+
+    def replayed(self):
+        """Account for one CUDA-graph replay of this plan (its kernels do not pass through the library's counter)."""
+        self.lib.graph_launches += self.n_kernels
 
     def profile(self, stream=None):
         """Run once with a CUDA-event pair around every launch; returns [(entry point, struct, ms)]."""
@@ -119,13 +126,15 @@ class Lib:
         if self.cdll.dtts_abi_version() != 1:
             raise DttsError("ABI version mismatch")
         self._plan = None
+        self.graph_launches = 0
 
     # -- info ------------------------------------------------------------------------------
     def last_error(self):
         return (self.cdll.dtts_last_error() or b"").decode()
 
     def launches(self):
-        return int(self.cdll.dtts_kernel_launches())
+        """Kernels of this library launched so far: direct launches + the kernels of replayed CUDA graphs."""
+        return int(self.cdll.dtts_kernel_launches()) + self.graph_launches
 
     def device_info(self):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

@@ -418,6 +418,7 @@ class _Engine:
         g = self._graphs.get(per_utt)
         if g is not None:
             g.replay()
+            plan.replayed()
             return self.out
         plan.run()
         # Small shards (e.g. 16 utterances per GPU at N=8) are launch-bound: ~150 launches of 10-20 us per eval.  Replay the

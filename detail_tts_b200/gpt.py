@@ -291,6 +291,7 @@ class _DecodeState:
     def run_step(self, use_graph):
         if self.graph is not None:
             self.graph.replay()
+            self.plan.replayed()
             return
         self._run_plan_pdl()         # eager at least once (one-time function attributes / tensor maps)
         self.eager_runs += 1
