@@ -559,7 +559,8 @@ class UnifiedVoice:
             n_gen = s + 1
             if s + 1 >= G:
                 break
-            if (s + 1) % sync_every == 0 or B == 1:
+            # early exit needs a host read of the finished flags; pointless while the stop token is suppressed
+            if suppress_token != STOP_MEL and ((s + 1) % sync_every == 0 or B == 1):
                 if int(st.unfinished.sum()) == 0:
                     break
             st.run_step(self.use_cuda_graph)
