@@ -28,9 +28,11 @@ class PackedConv:
         self.w_lo = w_lo
 
 
-def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None, split_k=1, bias=True, act_param=0.0):
-    """fp32-class GEMM on tcgen05 (3xTF32).  split_k > 1: out32 is a partial buffer [split_k, M, N]
-    (finish with splitk_reduce); otherwise the normal fused epilogue."""
+def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None, split_k=1, bias=True, act_param=0.0,
+                row_utt=None):
+    """fp32-class GEMM / multi-tap conv-GEMM on tcgen05 (3xTF32).  split_k > 1: out32 is a partial buffer
+    [split_k, M, N] (finish with splitk_reduce); otherwise the normal fused epilogue (bias, activation incl. the pair
+    gates, residual, separator rows)."""
     M = A_hi.shape[0]
     if split_k > 1:
         assert out32.dim() == 3 and out32.is_contiguous()
@@ -39,8 +41,8 @@ def gemm_tf32x3(A_hi, A_lo, pw, out32, res=None, act=ACT_NONE, out_row_map=None,
                         act=ACT_NONE, alpha=1.0, split_k=split_k, split_stride=out32.shape[1] * out32.shape[2])
         return
     _lib.lib().call("dtts_gemm_tf32x3", A=A_hi, A_lo=A_lo, W=pw.w, W_lo=pw.w_lo, M=M, N=pw.N, K=pw.K, lda=_ld(A_hi),
-                    ldw=_ld(pw.w), taps=1, tap_shift0=0, tap_stride=1, bias=pw.bias if bias else None,
-                    out_row_map=out_row_map, res=res, ldr=_ld(res) if res is not None else 0, out_f32=out32,
+                    ldw=_ld(pw.w), taps=pw.taps, tap_shift0=pw.shift0, tap_stride=pw.stride, bias=pw.bias if bias else None,
+                    out_row_map=out_row_map, row_utt=row_utt, res=res, ldr=_ld(res) if res is not None else 0, out_f32=out32,
                     ldo32=_ld(out32), act=act, act_param=act_param, alpha=1.0, split_k=1)
 
 

@@ -157,6 +157,15 @@ def pack_linear_tf32x3(w, b, device, n_pad=1):
     return pw
 
 
+def to_tf32x3(pw):
+    """Any fp32 PackedConv (linear or tap-major conv) -> operand pair for dtts_gemm_tf32x3: w = tf32-exact high part,
+    w_lo = the exact remainder."""
+    assert pw.w.dtype == torch.float32 and pw.K % 4 == 0
+    hi = (pw.w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    pw.w, pw.w_lo = hi.contiguous(), (pw.w - hi).contiguous()
+    return pw
+
+
 def pack_mrf_fragments(convs, cp, device):
     """[(w [C, C, k] fp32 (weight-norm folded), bias [C])] x 18 in dtts_voc_mrf order -> (w_frag uint8 tensor, bias [18, cp]).
     Per conv the fp16 weights are laid out as mma.sync m16n8k16 B fragments [tap][cp/8][cp/16][lane][4]:
