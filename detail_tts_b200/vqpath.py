@@ -23,7 +23,7 @@ class VQDecoder:
         table = torch.nn.functional.linear(emb, W[q + "project_out.weight"].float(), W[q + "project_out.bias"].float())
         self.bins, self.dim = table.shape
         self.table = torch.cat([table, torch.zeros(1, self.dim)], 0).to(device).contiguous()
-        self.ref = MelStyleEncoder(W, "vq_ref_enc.", torch.float32, device)   # fp32: its output is added to O(1) latents before a LayerNorm
+        self.ref = MelStyleEncoder(W, "vq_ref_enc.", torch.float32, device, tf32x3=True)   # fp32-class: its output is added to O(1) latents before a LayerNorm
         self.ln_g = W["vq_dec.1.weight"].to(device, torch.float32).contiguous()
         self.ln_b = W["vq_dec.1.bias"].to(device, torch.float32).contiguous()
         self.up1 = pack.pack_conv_transpose1d(W["vq_dec.3.weight"], W["vq_dec.3.bias"], F16, device, stride=2, padding=1)
