@@ -202,7 +202,6 @@ def main():
     from detail_tts_b200 import _lib, synth
     from detail_tts_b200 import dist as ddist
     from detail_tts_b200.model import SynthesizerTrn
-    import detail_tts_b200.diffusion as ddiff
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -11,7 +11,6 @@ is one multi-tap tcgen05 GEMM whose epilogue fuses bias, the speaker-conditionin
 fp16 operand, so no standalone elementwise pass touches HBM; ConvTranspose1d is a polyphase GEMM that
 writes the upsampled rows in place.  Residual streams are fp32, GEMM operands fp16.
 """
-import math
 import os
 
 import torch
