@@ -123,7 +123,7 @@ class Lib:
             n = self.cdll.dtts_sizeof(name.encode())
             if n != ctypes.sizeof(cls):
                 raise DttsError(f"ABI mismatch for {name}: header says {ctypes.sizeof(cls)}, library says {n}")
-        if self.cdll.dtts_abi_version() != 1:
+        if self.cdll.dtts_abi_version() != 2:
             raise DttsError("ABI version mismatch")
         self._plan = None
         self.graph_launches = 0

@@ -415,5 +415,6 @@ extern "C" int dtts_sizeof(const char* struct_name) {
   SZ(dtts_rowutt_params); SZ(dtts_copy_utts_params); SZ(dtts_split_params); SZ(dtts_reduce_params);
   SZ(dtts_voc_mrf_params); SZ(dtts_conv_post_params); SZ(dtts_stft_frames_params); SZ(dtts_spec_mag_params);
   SZ(dtts_gn_apply_params); SZ(dtts_zero_params); SZ(dtts_gpt_step_params);
+  SZ(dtts_dgemm_params); SZ(dtts_final_ln_params); SZ(dtts_decode_tail_params);
   return -1;
 }

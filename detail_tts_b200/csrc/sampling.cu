@@ -20,11 +20,35 @@ __device__ __forceinline__ uint32_t f2key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order == ascending uint order
 }
 
+// LayerNorm statistics of one row held in shared memory, in the format dtts_decode_gemm consumes: per 128-column group g,
+// stats[(g * n_rows + row) * 2 + {0, 1}] = (sum, sum of squared deviations from the group mean).  One warp per group.
+__device__ __forceinline__ void row_group_stats(const float* xs, int dim, float* stats, int row, int n_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int g = warp; g * 128 < dim; g += nw) {
+    float v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = xs[g * 128 + lane + 32 * i]; s += v[i]; }
+    s = warp_sum(s);
+    const float mean = s * (1.0f / 128.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float d = v[i] - mean; q += d * d; }
+    q = warp_sum(q);
+    if (lane == 0) { stats[((long)g * n_rows + row) * 2] = s; stats[((long)g * n_rows + row) * 2 + 1] = q; }
+  }
+}
+
+// TAIL = false: dtts_process_logits (dense probabilities / argmax out).  TAIL = true: dtts_decode_tail -- the token is
+// chosen on the device (argmax, or inverse-CDF sampling from a pre-drawn uniform) and appended (HF _sample bookkeeping +
+// next-step embedding + its LayerNorm statistics) by the same CTA; the last CTA to finish bumps the step counter.
+template <bool TAIL>
 __global__ void __launch_bounds__(PL_THREADS)
-process_logits_kernel(const dtts_logits_params p) {
+process_logits_kernel(const dtts_decode_tail_params p, int64_t* argmax_out) {
   pdl_launch();
   pdl_wait();
   extern __shared__ float sh[];          // [vocab] scores
+  __shared__ int sel_tok;
   __shared__ uint32_t bitmap[512];       // vocab <= 16384
   __shared__ uint32_t hist[256];
   __shared__ float red[40];
@@ -41,7 +65,8 @@ process_logits_kernel(const dtts_logits_params p) {
   for (int i = tid; i < 512; i += PL_THREADS) bitmap[i] = 0;
   __syncthreads();
   // repetition penalty: every distinct id of the history is penalised once (gather/scatter semantics)
-  const int n_ids = p.n_ids + (p.step_dev ? *p.step_dev : 0);
+  const int step = p.step_dev ? *p.step_dev : 0;
+  const int n_ids = p.n_ids + step;
   const int64_t* ids = p.ids + (long)row * p.ld_ids;
   for (int i = tid; i < n_ids; i += PL_THREADS) {
     const int id = (int)ids[i];
@@ -113,10 +138,11 @@ process_logits_kernel(const dtts_logits_params p) {
     if (tid == 0) {
       for (int w = 1; w < PL_THREADS / 32; ++w)
         if (red[w] > bv || (red[w] == bv && redi[w] < bi)) { bv = red[w]; bi = redi[w]; }
-      p.argmax[row] = bi;
+      if (argmax_out) argmax_out[row] = bi;
+      sel_tok = bi;
     }
-    return;
-  }
+    if (!TAIL) return;
+  } else {
 
   // temperature
   for (int i = tid; i < V; i += PL_THREADS) sh[i] = sh[i] / p.temperature;
@@ -218,11 +244,75 @@ process_logits_kernel(const dtts_logits_params p) {
     z_keep = Zk;
   }
   __syncthreads();
-  float* pr = p.probs + (long)row * p.ldp;
-  for (int i = tid; i < V; i += PL_THREADS) pr[i] = 0.f;
-  __syncthreads();
   const float mx = cand_v[0];
-  for (int i = tid; i < n_keep; i += PL_THREADS) pr[cand_i[i]] = expf(cand_v[i] - mx) / z_keep;
+  if (p.probs) {
+    float* pr = p.probs + (long)row * p.ldp;
+    for (int i = tid; i < V; i += PL_THREADS) pr[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < n_keep; i += PL_THREADS) pr[cand_i[i]] = expf(cand_v[i] - mx) / z_keep;
+  }
+  if (TAIL) {
+    // inverse-CDF sampling over the kept tokens in ascending id order (what a sequential fp32 cumulative sum over the
+    // dense probability row does): the first id whose cumulative probability exceeds u; the last kept id if none does.
+    float* sp = sh;                          // the score row is dead: reuse it ([0, nk) probabilities, [nk, 2nk) ids)
+    int* si = reinterpret_cast<int*>(sh + PL_MAX_CAND);
+    __syncthreads();
+    const int nk = n_keep;
+    for (int i = tid; i < nk; i += PL_THREADS) {
+      const int my = cand_i[i];
+      int r = 0;
+      for (int j = 0; j < nk; ++j) r += cand_i[j] < my;
+      sp[r] = expf(cand_v[i] - mx) / z_keep;
+      si[r] = my;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float u = p.uniforms[(long)step * p.ld_u + row];
+      float c = 0.f;
+      int tok = si[nk - 1];
+      for (int i = 0; i < nk; ++i) {
+        c += sp[i];
+        if (c > u) { tok = si[i]; break; }
+      }
+      sel_tok = tok;
+    }
+  }
+  }   // do_sample
+  if (!TAIL) return;
+
+  // ---- append (dtts_append_token's arithmetic) ----
+  __syncthreads();
+  __shared__ int64_t tok_s;
+  if (tid == 0) {
+    int64_t tok = sel_tok;
+    const int unf = p.unfinished[row];
+    if (!unf) tok = p.stop_token;
+    p.ids[(long)row * p.ld_ids + p.n_ids + step] = tok;
+    p.unfinished[row] = unf && (tok != p.stop_token);
+    const int pos0 = p.kv_pos_rows ? p.kv_pos_rows[row] : 0;
+    if (p.kv_row) p.kv_row[row] = row * p.kv_stride + pos0 + step;
+    if (p.kv_len) p.kv_len[row] = pos0 + step + 1;
+    tok_s = tok;
+  }
+  __syncthreads();
+  if (p.x_out) {
+    const float* te = p.tok_emb + tok_s * p.dim;
+    const float* pe = p.pos_emb + (long)(p.pos + step) * p.dim;
+    float* xo = p.x_out + (long)row * p.ldx;
+    for (int d = tid; d < p.dim; d += PL_THREADS) { const float v = te[d] + pe[d]; xo[d] = v; sh[d] = v; }
+    __syncthreads();
+    if (p.x_stats) row_group_stats(sh, p.dim, p.x_stats, row, p.n_rows);
+  }
+  // the last row to arrive advances the step counter (every row has read it before arriving)
+  __syncthreads();
+  if (tid == 0 && p.done_counter) {
+    __threadfence();
+    const unsigned prev = atomicAdd(p.done_counter, 1u);
+    if (prev == (unsigned)p.n_rows - 1u) {
+      *p.done_counter = 0u;
+      if (p.step_dev) *p.step_dev = step + 1;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -246,10 +336,19 @@ append_token_kernel(const dtts_append_params p) {
   __syncthreads();
   const int64_t tok = tok_s;
   if (p.x_out) {
+    __shared__ float xrow[1024];
     const float* te = p.tok_emb + tok * p.dim;
     const float* pe = p.pos_emb + (long)(p.pos + step) * p.dim;
     float* xo = p.x_out + (long)row * p.ldx;
-    for (int d = threadIdx.x; d < p.dim; d += blockDim.x) xo[d] = te[d] + pe[d];
+    for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
+      const float v = te[d] + pe[d];
+      xo[d] = v;
+      if (p.x_stats) xrow[d] = v;
+    }
+    if (p.x_stats) {
+      __syncthreads();
+      row_group_stats(xrow, p.dim, p.x_stats, row, p.n_rows);
+    }
   }
 }
 
@@ -263,14 +362,34 @@ extern "C" int dtts_process_logits(const dtts_logits_params* p, void* stream) {
   DTTS_REQUIRE(p->do_sample ? (p->probs != nullptr) : (p->argmax != nullptr), "process_logits: missing output");
   DTTS_REQUIRE(!p->do_sample || (p->temperature > 0.f && p->top_k > 0 && p->top_k <= 512), "process_logits: bad sampling params");
   if (p->n_rows <= 0) return 0;
-  launch_maybe_pdl(process_logits_kernel, dim3(p->n_rows), dim3(PL_THREADS), p->vocab * sizeof(float), (cudaStream_t)stream, *p);
+  dtts_decode_tail_params t;
+  memset(&t, 0, sizeof(t));
+  t.logits = p->logits; t.ldl = p->ldl; t.n_rows = p->n_rows; t.vocab = p->vocab;
+  t.ids = const_cast<int64_t*>(p->ids); t.ld_ids = p->ld_ids; t.n_ids = p->n_ids; t.step_dev = const_cast<int*>(p->step_dev);
+  t.penalty = p->penalty; t.temperature = p->temperature; t.top_p = p->top_p; t.top_k = p->top_k;
+  t.do_sample = p->do_sample; t.suppress_token = p->suppress_token; t.typical_mass = p->typical_mass;
+  t.probs = p->probs; t.ldp = p->ldp;
+  launch_maybe_pdl(process_logits_kernel<false>, dim3(p->n_rows), dim3(PL_THREADS), p->vocab * sizeof(float), (cudaStream_t)stream, t, p->argmax);
   DTTS_CHECK_LAUNCH("process_logits");
+  return 0;
+}
+
+extern "C" int dtts_decode_tail(const dtts_decode_tail_params* p, void* stream) {
+  DTTS_REQUIRE(p && p->logits && p->ids && p->unfinished && p->step_dev && p->done_counter, "decode_tail: null argument");
+  DTTS_REQUIRE(p->vocab >= 2 * PL_MAX_CAND && p->vocab <= 16384, "decode_tail: vocab out of range");
+  DTTS_REQUIRE(!p->do_sample || (p->uniforms && p->temperature > 0.f && p->top_k > 0 && p->top_k <= 512), "decode_tail: bad sampling params");
+  DTTS_REQUIRE(!p->x_out || (p->tok_emb && p->pos_emb && p->dim <= p->vocab), "decode_tail: missing embedding tables");
+  DTTS_REQUIRE(!p->x_stats || (p->x_out && p->dim % 128 == 0), "decode_tail: x_stats needs x_out and dim %% 128 == 0");
+  if (p->n_rows <= 0) return 0;
+  launch_maybe_pdl(process_logits_kernel<true>, dim3(p->n_rows), dim3(PL_THREADS), p->vocab * sizeof(float), (cudaStream_t)stream, *p, (int64_t*)nullptr);
+  DTTS_CHECK_LAUNCH("decode_tail");
   return 0;
 }
 
 extern "C" int dtts_append_token(const dtts_append_params* p, void* stream) {
   DTTS_REQUIRE(p && p->next && p->ids && p->unfinished, "append_token: null argument");
   DTTS_REQUIRE(!p->x_out || (p->tok_emb && p->pos_emb), "append_token: missing embedding tables");
+  DTTS_REQUIRE(!p->x_stats || (p->x_out && p->dim % 128 == 0 && p->dim <= 1024), "append_token: x_stats needs x_out and dim %% 128 == 0, dim <= 1024");
   if (p->n_rows <= 0) return 0;
   append_token_kernel<<<p->n_rows, 256, 0, (cudaStream_t)stream>>>(*p);
   DTTS_CHECK_LAUNCH("append_token");

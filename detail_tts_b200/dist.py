@@ -70,10 +70,11 @@ def gather_waveforms(wav, wav_lengths, shards, max_samples, device, dst=0):
     per = max(len(s) for s in shards)
     buf = torch.zeros(per, max_samples, dtype=torch.float32, device=device)
     n = wav.shape[0]
-    S = min(wav.shape[-1], max_samples)
-    buf[:n, :S] = wav.reshape(n, -1)[:, :S].to(device)
     ln = torch.zeros(per, dtype=torch.int64, device=device)
-    ln[:n] = wav_lengths.to(device)
+    if n:                                  # a rank with an empty shard (B < world size) still takes part in the gathers
+        S = min(wav.shape[-1], max_samples)
+        buf[:n, :S] = wav.reshape(n, wav.shape[-1])[:, :S].to(device)
+        ln[:n] = wav_lengths.to(device).clamp(max=max_samples)     # the waveforms are truncated to max_samples: so are the lengths
     outs = [torch.empty_like(buf) for _ in range(ws)] if rank == dst else None
     louts = [torch.empty_like(ln) for _ in range(ws)] if rank == dst else None
     dist.gather(buf, outs, dst=dst)

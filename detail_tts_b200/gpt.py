@@ -12,6 +12,7 @@ followed on-device by the HF processor chain (sampling.cu) with no per-token hos
 Numerics: fp32 operands/accumulation by default (token-exact sampling needs fp32-class logits,
 SURVEY.md section 7); `dtype=torch.float16` selects the tcgen05 path.
 """
+import collections
 import math
 import os
 
@@ -30,6 +31,12 @@ FUSE_QKV_REDUCE = os.environ.get("DTTS_FUSE_QKV", "1") != "0"
 # Measured per step as one CUDA graph (B200): B=1 0.45 ms vs 0.64 ms kernel by kernel, B=4 0.47 vs 0.61; B=16 0.65 vs 0.63;
 # B=32 0.98 vs 0.66 -- the ~52 grid barriers cost ~3.5 us each and the per-row work grows faster than on the tensor cores.
 MEGA_MAX_B = int(os.environ.get("DTTS_GPT_MEGA_MAX_B", "4"))
+# decode step for 5..128 utterances on the fused decode GEMMs (csrc/gpt_dgemm.cu): LayerNorm + operand split inside the GEMM,
+# split-K summed through cluster shared memory, 5 launches per block instead of 8 (53 per step instead of 84).
+FUSED_STEP = os.environ.get("DTTS_GPT_FUSED", "1") != "0"
+FUSED_MAX_B = int(os.environ.get("DTTS_GPT_FUSED_MAX_B", "64"))   # measured (B200): fused 483 / 540 / 627 / 900 us per step at 16 / 32 / 64 / 128 utterances vs 655 / 664 / 694 / 828
+# cluster sizes (= K splits) of the fused step's GEMMs: c_attn, attn c_proj, c_fc, mlp c_proj, mel_head
+FUSED_SPLITS = tuple(int(v) for v in os.environ.get("DTTS_GPT_FUSED_SPLITS", "4,8,4,8,2").split(","))
 
 
 def _i32(x, device):
@@ -179,9 +186,14 @@ class _DecodeState:
     recorded launch Plan over these buffers (position / history length come from the device-side `step`), which
     is what makes it capturable into ONE CUDA graph and replayable with no per-token marshalling."""
 
+    @staticmethod
+    def arena_bytes(B, Pmax, G, n_mel0):
+        return N_LAYERS * B * (Pmax + n_mel0 + G) * 3 * D_MODEL * 4
+
     def __init__(self, gpt, B, Pmax, G, sampling, n_mel0=1):
         """n_mel0: mel tokens already in the sequence when decoding starts: 1 (<start_mel>) for
         inference_speech_tortoise, 2 + len(mel_codes) for inference_speech_valle."""
+        self.nbytes = self.arena_bytes(B, Pmax, G, n_mel0)
         do_sample, penalty, temperature, top_p, top_k, suppress_token, typical_mass = sampling
         self.gpt, self.B, self.G, self.n_mel0 = gpt, B, G, n_mel0
         dev, dt = gpt.device, gpt.dtype
@@ -249,6 +261,14 @@ class _DecodeState:
                      pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
                      kv_pos_rows=self.kv_base)
         self.mega = gpt.tf32x3 and B <= min(MEGA_MAX_B, 32)
+        self.fused = gpt.tf32x3 and FUSED_STEP and not self.mega and B <= FUSED_MAX_B
+        self.loop_plan = self.tail_plan = None
+        self.loop_graph = None
+        if self.fused:
+            self._init_fused(sampling)
+            self.graph = None
+            self.eager_runs = 0
+            return
         with lib.record() as self.plan:
             if self.mega:
                 # one persistent kernel for the whole step (fp32 weights = hi + lo of the 3xTF32 packing, exact)
@@ -309,8 +329,91 @@ class _DecodeState:
                 ops.layernorm(xs, *T.ln_f, out32=t32)
             if not self.mega:
                 head()
+        if gpt.tf32x3 and not self.mega and B <= 128:
+            # device-side token choice for the kernel-by-kernel step too (more than FUSED_MAX_B utterances): dtts_decode_tail +
+            # the split-K step + final_norm with latent capture + the swap-AB mel_head GEMM; no host work per token
+            self.uniforms = torch.zeros(G, B, dtype=torch.float32, device=dev)
+            self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+
+            def tail():
+                lib.call("dtts_decode_tail", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
+                         n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                         do_sample=int(do_sample), suppress_token=suppress_token, typical_mass=typical_mass, probs=None, ldp=0,
+                         uniforms=self.uniforms, ld_u=B, unfinished=self.unfinished, stop_token=STOP_MEL,
+                         tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos, pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL,
+                         x_stats=None, kv_row=kv_row, kv_stride=stride, kv_len=kv_len, kv_pos_rows=self.kv_base,
+                         done_counter=self.done)
+            with lib.record() as self.tail_plan:
+                tail()
+            with lib.record() as self.loop_plan:
+                tail()
+                self.loop_plan.calls.extend(self.plan.calls[:-3])        # the step up to ln_f (t32); its head is replaced below
+                self.loop_plan.keep.extend(self.plan.keep)
+                ops.final_ln(t32, gpt.final_norm, None, hn, lat=self.latents, lat_pos0=0, step_dev=self.step)
+                ops.decode_gemm(hn, gpt.mel_head, self.logits, B, k_splits=FUSED_SPLITS[4], N=VOCAB)
         self.graph = None
         self.eager_runs = 0
+
+    def _init_fused(self, sampling):
+        """The fused decode step (csrc/gpt_dgemm.cu).  Per block: [ln_1 + c_attn -> KV arena] -> cached attention ->
+        [c_proj + residual (+ ln_2 statistics)] -> [ln_2 + c_fc + gelu_new] -> [mlp c_proj + residual (+ ln_1 statistics)];
+        then ln_f + final_norm (+ latent capture) -> mel_head.  Two plans share these launches:
+          plan       the step alone + dtts_process_logits: the host draws the token (multinomial hook of the parity tests)
+          loop_plan  dtts_decode_tail (processors + argmax / inverse-CDF sampling + append) + the step: no host work per token."""
+        do_sample, penalty, temperature, top_p, top_k, suppress_token, typical_mass = sampling
+        gpt, B, G, n_mel0 = self.gpt, self.B, self.G, self.n_mel0
+        dev = gpt.device
+        lib = ops._lib.lib()
+        T = gpt.trunk
+        e = lambda *shape, d=torch.float32: torch.empty(*shape, dtype=d, device=dev)  # noqa: E731
+        xs, hn, arena, kv_row, kv_len, k_off, stride = self.xs, self.hn, self.arena, self.kv_row, self.kv_len, self.k_off, self.stride
+        self.att, self.u = att, u = e(B, D_MODEL), e(B, 4 * D_MODEL)
+        self.st_a, self.st_b = st_a, st_b = torch.zeros(D_MODEL // 128, B, 2, device=dev), torch.zeros(D_MODEL // 128, B, 2, device=dev)
+        self.uniforms = torch.zeros(G, B, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+        iota = torch.arange(B, dtype=torch.int32, device=dev)
+        ones = torch.ones(B, dtype=torch.int32, device=dev)
+        LDL = self.logits.shape[1]
+        ld_ids, n_ids0 = self.ld_ids, self.n_ids0
+        S = FUSED_SPLITS
+
+        def step():
+            for l, ly in enumerate(T.layers):
+                ops.decode_gemm(xs, ly["attn"], arena[l], B, ln=ly["ln1"], ln_stats=st_a, out_row_map=kv_row, k_splits=S[0])
+                ops.attention(arena[l], arena[l][:, D_MODEL:], arena[l][:, 2 * D_MODEL:], N_HEADS, HEAD_DIM, kv_row, ones, k_off,
+                              kv_len, 1, stride, HEAD_DIM ** -0.5, o_off=iota, out32=att)
+                ops.decode_gemm(att, ly["proj"], xs, B, res=xs, out_stats=st_b, k_splits=S[1])
+                ops.decode_gemm(xs, ly["fc"], u, B, ln=ly["ln2"], ln_stats=st_b, act=ops.ACT_GELU_NEW, k_splits=S[2])
+                ops.decode_gemm(u, ly["out"], xs, B, res=xs, out_stats=st_a, k_splits=S[3])
+            ops.final_ln(xs, T.ln_f, gpt.final_norm, hn, lat=self.latents, lat_pos0=0, step_dev=self.step)
+            ops.decode_gemm(hn, gpt.mel_head, self.logits, B, k_splits=S[4], N=VOCAB)
+
+        def tail():
+            lib.call("dtts_decode_tail", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
+                     n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                     do_sample=int(do_sample), suppress_token=suppress_token, typical_mass=typical_mass, probs=None, ldp=0,
+                     uniforms=self.uniforms, ld_u=B, unfinished=self.unfinished, stop_token=STOP_MEL,
+                     tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos, pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL,
+                     x_stats=st_a, kv_row=kv_row, kv_stride=stride, kv_len=kv_len, kv_pos_rows=self.kv_base,
+                     done_counter=self.done)
+
+        with lib.record() as self.plan:
+            step()
+            lib.call("dtts_process_logits", logits=self.logits, ldl=LDL, n_rows=B, vocab=VOCAB, ids=self.ids, ld_ids=ld_ids,
+                     n_ids=n_ids0, step_dev=self.step, penalty=penalty, temperature=temperature, top_p=top_p, top_k=top_k,
+                     do_sample=int(do_sample), suppress_token=suppress_token, probs=self.probs, ldp=VOCAB, argmax=self.argmax,
+                     typical_mass=typical_mass)
+        with lib.record() as self.tail_plan:
+            tail()
+        with lib.record() as self.loop_plan:
+            tail()
+            step()
+        # the append of the host-sampling path also has to emit the ln_1 statistics of the new embedding row
+        with lib.record() as self.append_plan:
+            lib.call("dtts_append_token", n_rows=B, next=self.nxt, ids=self.ids, ld_ids=ld_ids, n_ids=n_ids0, step_dev=self.step,
+                     unfinished=self.unfinished, stop_token=STOP_MEL, tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos,
+                     pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL, kv_row=kv_row, kv_stride=stride, kv_len=kv_len,
+                     kv_pos_rows=self.kv_base, x_stats=st_a)
 
     def reset(self, P, mel_prefix):
         """Per-call reset: history ids (fake 1's, then the mel tokens the sequence starts with), finished flags, step
@@ -319,37 +422,49 @@ class _DecodeState:
         self.ids[:, self.n_ids0 - self.n_mel0:self.n_ids0] = mel_prefix
         self.unfinished.fill_(1)
         self.step.zero_()
+        if self.loop_plan is not None:
+            self.done.zero_()
         self.kv_base.copy_(torch.tensor([p + self.n_mel0 for p in P], dtype=torch.int32), non_blocking=False)
 
-    def _run_plan_pdl(self):
-        """The decode step's launches with programmatic dependent launch between them (see dtts_set_pdl)."""
+    def _run_plan_pdl(self, plan):
+        """A plan's launches with programmatic dependent launch between them (see dtts_set_pdl)."""
         cdll = ops._lib.lib().cdll
-        old = cdll.dtts_set_pdl(1 if self.gpt.use_pdl else 0)
+        pdl = self.gpt.use_pdl_fused if self.fused else self.gpt.use_pdl
+        old = cdll.dtts_set_pdl(1 if pdl else 0)
         try:
-            self.plan.run()
+            plan.run()
         finally:
             cdll.dtts_set_pdl(old)
 
-    def run_step(self, use_graph):
-        if self.graph is not None:
-            self.graph.replay()
-            self.plan.replayed()
+    def _run_or_replay(self, plan, graph_attr, use_graph):
+        g = getattr(self, graph_attr)
+        if g is not None:
+            g.replay()
+            plan.replayed()
             return
-        self._run_plan_pdl()         # eager at least once (one-time function attributes / tensor maps)
-        self.eager_runs += 1
-        if use_graph and self.eager_runs >= 1:
+        self._run_plan_pdl(plan)     # eager at least once (one-time function attributes / tensor maps)
+        if use_graph:
             # capture WITHOUT torch.cuda.graph(): its __enter__ calls empty_cache(), which would make every later
-            # stage of the pipeline re-cudaMalloc its buffers on every call.
+            # stage of the pipeline re-cudaMalloc its buffers on every call.  The capture only records: the eager run
+            # above already produced this step's results, and recording a plan does not execute it.
             g = torch.cuda.CUDAGraph()
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 g.capture_begin()
-                self._run_plan_pdl()
+                self._run_plan_pdl(plan)
                 g.capture_end()
             cur.wait_stream(side)
-            self.graph = g
+            setattr(self, graph_attr, g)
+
+    def run_step(self, use_graph):
+        """One decode step; the token was appended by the host-driven path (append_plan)."""
+        self._run_or_replay(self.plan, "graph", use_graph)
+
+    def run_loop(self, use_graph):
+        """Fused step only: choose + append the next token on the device, then the step that consumes it."""
+        self._run_or_replay(self.loop_plan, "loop_graph", use_graph)
 
 
 class UnifiedVoice:
@@ -376,10 +491,14 @@ class UnifiedVoice:
                                                     tf32x3=self.tf32x3 and os.environ.get("DTTS_COND_TF32X3", "1") != "0")
         self.max_mel_positions = self.mel_pos.shape[0]
         self.last_latents = None
+        self.last_uniforms = None       # [G, B] uniforms the in-graph sampler consumed in the last call (parity checks)
         self.last_lengths = None
         self.use_cuda_graph = True      # replay the ~95-launch decode step as one CUDA graph
         self.use_pdl = os.environ.get("DTTS_PDL", "0") != "0"   # programmatic dependent launch between the step's kernels (measured: no gain, 1185 vs 1132 us)
-        self._states = {}
+        # ... of the fused step: there the weight TMA loads of kernel N+1 are issued before its griddepcontrol.wait
+        self.use_pdl_fused = os.environ.get("DTTS_PDL_FUSED", "1") != "0"
+        self.device_sampling = os.environ.get("DTTS_DEVICE_SAMPLING", "1") != "0"
+        self._states = collections.OrderedDict()      # LRU of decode workspaces under a byte budget
         self._mega_w = None
 
     # ------------------------------------------------------------------------------------------
@@ -518,7 +637,7 @@ class UnifiedVoice:
     @torch.no_grad()
     def inference_speech_tortoise(self, speech_conditioning_latent, cond_lengths, text_inputs, input_tokens=None,
                                   num_return_sequences=1, max_generate_length=None, typical_sampling=False,
-                                  typical_mass=.9, text_lengths=None, multinomial=None, sync_every=8,
+                                  typical_mass=.9, text_lengths=None, multinomial=None, sync_every=8, logits_hook=None,
                                   **hf_generate_kwargs):
         """gpt/model.py:514-545.  Returns codes [B, G<=max_generate_length] (rows padded with 8193
         after EOS), as HF generate()[:, trunc_index:] does.  Supported generate kwargs are the ones the
@@ -526,12 +645,13 @@ class UnifiedVoice:
         default 50), repetition_penalty, length_penalty (ignored when sampling, as in HF),
         suppress_tokens=[8193]; `typical_sampling=True` inserts the reference's TypicalLogitsWarper(mass=typical_mass)
         (gpt/modules/typical_sampling.py) after the repetition penalty, where HF puts custom processors.
-        `multinomial(probs)->[B,1]` overrides torch.multinomial (tests)."""
+        `multinomial(probs)->[B,1]` overrides the token draw and `logits_hook(step, logits [B, vocab])` observes the raw
+        logits of every step (parity tests); either one selects the host-driven loop instead of the in-graph sampler."""
         B = text_inputs.shape[0]
         start = torch.full((B, 1), START_MEL, dtype=torch.long, device=self.device)
         return self._sample_codes(speech_conditioning_latent, cond_lengths, text_inputs, start, input_tokens,
                                   num_return_sequences, max_generate_length, typical_sampling, typical_mass, text_lengths,
-                                  multinomial, sync_every, hf_generate_kwargs)
+                                  multinomial, sync_every, hf_generate_kwargs, logits_hook)
 
     def inference_speech_valle(self, speech_conditioning_latent, cond_lengths, text_inputs, mel_codes, input_tokens=None,
                                num_return_sequences=1, max_generate_length=None, typical_sampling=False, typical_mass=.9,
@@ -551,7 +671,7 @@ class UnifiedVoice:
 
     def _sample_codes(self, speech_conditioning_latent, cond_lengths, text_inputs, mel_prefix, input_tokens,
                       num_return_sequences, max_generate_length, typical_sampling, typical_mass, text_lengths, multinomial,
-                      sync_every, hf_generate_kwargs):
+                      sync_every, hf_generate_kwargs, logits_hook=None):
         """KV-cached HF-style sampling shared by the two entry points; `mel_prefix` [B, n_mel0] are the mel tokens the
         sequence starts with (their embeddings go through the prefill, their ids into the repetition-penalty set)."""
         assert input_tokens is None and num_return_sequences == 1, \
@@ -592,22 +712,46 @@ class UnifiedVoice:
         st.latents[:, 0].copy_(st.hn)
 
         n_gen = 0
-        for s in range(G):
+        if st.loop_plan is not None and multinomial is None and logits_hook is None and self.device_sampling:
+            # no host work per token: processors + token choice + append run inside the step's CUDA graph.  Sampling is an
+            # inverse-CDF draw from uniforms drawn here in one call (torch's CUDA generator: torch.manual_seed applies), i.e. a
+            # different random stream than HF's per-step torch.multinomial (the parity tests inject the reference's draws
+            # through `multinomial`, which takes the host-driven path below).
             if do_sample:
-                nxt = (multinomial(st.probs) if multinomial is not None else torch.multinomial(st.probs, 1)).reshape(B)
-                st.nxt.copy_(nxt)
-            else:
-                st.nxt.copy_(st.argmax)
-            st.append_plan.run()     # ids[:, n_ids0+s] = token s; xs = emb(token s) + mel_pos[s+1]; KV row/len; step++
-            n_gen = s + 1
-            if s + 1 >= G:
-                break
-            # early exit needs a host read of the finished flags; pointless while the stop token is suppressed
-            if suppress_token != STOP_MEL and ((s + 1) % sync_every == 0 or B == 1):
-                if int(st.unfinished.sum()) == 0:
+                st.uniforms[:G].copy_(torch.rand(G, B, device=dev))
+                self.last_uniforms = st.uniforms[:G]
+            for s in range(G):
+                last = s + 1 >= G
+                if last:
+                    st.tail_plan.run()
+                else:
+                    st.run_loop(self.use_cuda_graph)
+                n_gen = s + 1
+                if last:
                     break
-            st.run_step(self.use_cuda_graph)
-            st.latents[:, s + 1].copy_(st.hn)
+                if suppress_token != STOP_MEL and ((s + 1) % sync_every == 0 or B == 1):
+                    if int(st.unfinished.sum()) == 0:
+                        break
+        else:
+            for s in range(G):
+                if logits_hook is not None:
+                    logits_hook(s, st.logits[:, :VOCAB])
+                if do_sample:
+                    nxt = (multinomial(st.probs) if multinomial is not None else torch.multinomial(st.probs, 1)).reshape(B)
+                    st.nxt.copy_(nxt)
+                else:
+                    st.nxt.copy_(st.argmax)
+                st.append_plan.run()     # ids[:, n_ids0+s] = token s; xs = emb(token s) + mel_pos[s+1]; KV row/len; step++
+                n_gen = s + 1
+                if s + 1 >= G:
+                    break
+                # early exit needs a host read of the finished flags; pointless while the stop token is suppressed
+                if suppress_token != STOP_MEL and ((s + 1) % sync_every == 0 or B == 1):
+                    if int(st.unfinished.sum()) == 0:
+                        break
+                st.run_step(self.use_cuda_graph)
+                if not st.fused:
+                    st.latents[:, s + 1].copy_(st.hn)     # (the fused step's final_ln kernel stores the latent itself)
         codes = st.ids[:, st.n_ids0:st.n_ids0 + n_gen].clone()
         # trim trailing all-pad columns produced between host checks
         if n_gen > 1:
@@ -623,12 +767,20 @@ class UnifiedVoice:
         """Persistent decode workspace (KV arena, step buffers, recorded launch plans, captured CUDA graph) for one
         (batch, prefix capacity, generation cap, sampling config): reused across calls, so the per-call cost is a
         few small resets instead of re-recording / re-capturing ~95 launches."""
-        key = (B, Pmax, G, sampling, n_mel0)
+        # capacities are bucketed (rows are right-aligned and length-masked, so a larger prefix / generation capacity changes
+        # nothing): real traffic with varying text lengths reuses one state instead of re-recording and re-capturing the graph
+        Pcap = -(-Pmax // 16) * 16
+        Gcap = max(G, min(-(-G // 64) * 64, self.max_mel_positions - 1 - n_mel0))
+        key = (B, Pcap, Gcap, sampling, n_mel0)
         st = self._states.get(key)
-        if st is None:
-            if len(self._states) >= 4:
-                self._states.clear()
-            st = self._states[key] = _DecodeState(self, B, Pmax, G, sampling, n_mel0)
+        if st is not None:
+            self._states.move_to_end(key)
+            return st
+        need = _DecodeState.arena_bytes(B, Pcap, Gcap, n_mel0)
+        budget = float(os.environ.get("DTTS_GPT_STATE_BYTES", 24e9))
+        while self._states and sum(v.nbytes for v in self._states.values()) + need > budget:   # least recently used first
+            self._states.popitem(last=False)
+        st = self._states[key] = _DecodeState(self, B, Pcap, Gcap, sampling, n_mel0)
         return st
 
     inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528
@@ -645,7 +797,7 @@ class UnifiedVoice:
         assert return_latent, "only return_latent=True is on the synthesis path"
         dev = self.device
         B, Tm = mel_codes.shape
-        tl = self._text_lengths(text_inputs, None)
+        tl = self._text_lengths(text_inputs, text_lengths)     # per-utterance text lengths (None = the padded width, as the reference's B=1 call)
         ml = [Tm] * B if mel_lengths is None else [int(v) for v in mel_lengths]
         cond = self.get_conditioning(speech_conditioning_latent.to(dev), cond_lengths)
         mc = mel_codes.to(dev, torch.long)

@@ -88,11 +88,26 @@ class SynthesizerTrn:
         codes, T, tl, rl, refer = self._generate_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample,
                                                        suppress_eos, hooks)
         mark("gpt")
-        assert min(T) >= 1, "an utterance produced no codes"
+        # An utterance whose FIRST sampled token is the stop token has no codes: the reference's `infer` has no defined output
+        # for it (codes[:, :-1] is empty, model_24k.py:795-803 then fails inside the diffusion model).  Here it yields an empty
+        # waveform (length 0) and the rest of the batch is synthesised as usual.
+        keep = [b for b in range(len(T)) if T[b] >= 1]
+        B_all, T_all = len(T), T
+        if not keep:
+            if trace is not None:
+                trace.update(codes=codes, T=T_all)
+            return torch.zeros(B_all, 1, 0, device=dev), torch.zeros(B_all, dtype=torch.long, device=dev)
+        sel = None
+        if len(keep) < B_all:
+            sel = torch.tensor(keep, dtype=torch.long, device=dev)
+            T = [T_all[b] for b in keep]
+            tl, rl = [tl[b] for b in keep], [rl[b] for b in keep]
+            text, refer, codes = text.to(dev)[sel], refer[sel], codes[sel]
         Tmax = max(T)
         codes = codes[:, :Tmax]
         if self.capture_latents:
-            latent = self.gpt.last_latents[:, :Tmax].contiguous()
+            latent = self.gpt.last_latents[:, :Tmax] if sel is None else self.gpt.last_latents[sel, :Tmax]
+            latent = latent.contiguous()
         else:
             latent = self.gpt.forward(refer, rl, text, tl, codes, None, return_latent=True, clip_inputs=False,
                                       mel_lengths=T)
@@ -107,6 +122,11 @@ class SynthesizerTrn:
         y_lengths = [4 * t for t in T]
         wav = self.flowvae.infer(mel, y_lengths, noise_scale=noise_scale, randn_like=hooks.get("randn_like_zp"))
         mark("flowvae_vocoder")
+        if sel is not None:                # rows of the empty utterances: zero waveform, length 0
+            full = torch.zeros(B_all, 1, wav.shape[-1], dtype=wav.dtype, device=dev)
+            full[sel] = wav
+            wav = full
+            T = T_all
         if trace is not None:
             trace.update(codes=codes, T=T, latent=latent, cond=cond, mel=mel)
             if marks:

@@ -66,6 +66,24 @@ def splitk_reduce(ws, n_splits, M, N, bias=None, act=ACT_NONE, res=None, out32=N
                     ld_hl=_ld(y_hi) if y_hi is not None else 0)
 
 
+def decode_gemm(x, pw, out, B, ln=None, ln_stats=None, act=ACT_NONE, res=None, out_row_map=None, out_stats=None, k_splits=8,
+                N=None, bias=True):
+    """One GEMM of the fused decode step (csrc/gpt_dgemm.cu): out[b] = act(LN(x[b]) @ W^T + bias) + res[b] for b < B <= 128.
+    `ln` = (gamma, beta) with `ln_stats` [parts, B, 2] from the producer (`out_stats` of the previous dgemm / dtts_append_token)."""
+    _lib.lib().call("dtts_decode_gemm", x=x, ldx=_ld(x), W_hi=pw.w, W_lo=pw.w_lo, ldw=_ld(pw.w), w_rows=pw.w.shape[0], B=B,
+                    N=pw.N if N is None else N, K=pw.K, ln_stats=ln_stats, ln_parts=ln_stats.shape[0] if ln_stats is not None else 0,
+                    ln_gamma=ln[0] if ln else None, ln_beta=ln[1] if ln else None, ln_eps=1e-5,
+                    bias=pw.bias if bias else None, act=act, res=res, ldr=_ld(res) if res is not None else 0, out=out, ldo=_ld(out),
+                    out_row_map=out_row_map, out_stats=out_stats, k_splits=k_splits)
+
+
+def final_ln(x, ln1, ln2, y, lat=None, lat_pos0=0, step_dev=None):
+    """ln_f -> final_norm of the B new rows (+ latent capture at position lat_pos0 + *step_dev of lat [B, T, C])."""
+    _lib.lib().call("dtts_final_ln", x=x, ldx=_ld(x), B=x.shape[0], C=x.shape[1], g1=ln1[0], b1=ln1[1],
+                    g2=ln2[0] if ln2 else None, b2=ln2[1] if ln2 else None, eps=1e-5, y=y, ldy=_ld(y), lat=lat,
+                    lat_stride_b=lat.stride(0) if lat is not None else 0, lat_pos0=lat_pos0, step_dev=step_dev)
+
+
 def split_tf32(x, hi, lo):
     _lib.lib().call("dtts_split_tf32", x=x, ldx=_ld(x), M=x.shape[0], C=x.shape[1], hi=hi, lo=lo, ld=_ld(hi))
 

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DTTS_ABI_VERSION 1
+#define DTTS_ABI_VERSION 2
 
 /* activations usable in GEMM epilogues / elementwise kernels */
 enum {
@@ -219,10 +219,72 @@ typedef struct {
   int* kv_row; int kv_stride;    /* optional [n_rows]: kv_row[b] = b*kv_stride + kv_pos0 + step (next KV/out row) */
   int kv_pos0; int* kv_len;      /* optional [n_rows]: kv_len[b] = kv_pos0 + step + 1 (keys visible next step) */
   const int* kv_pos_rows;        /* optional [n_rows]: per-row base position used instead of kv_pos0 (varlen prefixes) */
+  float* x_stats;                /* optional [dim/128, n_rows, 2]: (sum, centred sum of squares) of every 128-column group of
+                                    x_out -- the LayerNorm statistics format dtts_decode_gemm consumes (ln_stats) */
 } dtts_append_params;
 /* HF _sample bookkeeping (generation/utils.py:2797-2805) + next-token embedding
  * mel_embedding[id] + mel_pos_embedding[pos] (gpt/model.py:145-148). */
 int dtts_append_token(const dtts_append_params* p, void* stream);
+
+/* ---- the fused KV-cached decode step (round 2): 5 launches per GPT2Block instead of 8, no split-K partial buffers ------
+ * dtts_decode_gemm: out[b, n] = act( sum_k LN(x)[b, k] * W[n, k] + bias[n] ) + res[b, n] for the B <= 128 utterance rows of
+ * one decode step (HF GPT2Block's c_attn / c_proj / c_fc / mlp.c_proj and gpt/model.py:324 mel_head), "swap-AB" on tcgen05:
+ * a 128-row slab of W is the M operand (TMA-staged, 128B swizzle), the activation rows are the N operand (N = B padded to
+ * 16/32/64/128), 3xTF32 (hi*hi + lo*hi + hi*lo) with fp32 accumulators in TMEM.  The operand split x = hi + lo and the
+ * optional LayerNorm in front of the GEMM (ln_1 / ln_2: transformers modeling_gpt2.py:262-310) happen while the activation
+ * tile is written to shared memory, so there are no LayerNorm / split / reduce launches.  K is split over the CTAs of one
+ * thread-block cluster (k_splits = 1, 2, 4 or 8); the partial accumulators are summed through distributed shared memory in
+ * a fixed order (deterministic), each CTA finishing B/k_splits rows.  The weight TMA loads are issued before
+ * griddepcontrol.wait, so under programmatic dependent launch (dtts_set_pdl) they overlap the predecessor's tail. */
+typedef struct {
+  const float* x; int ldx;               /* [B, K] fp32 activations */
+  const float* W_hi; const float* W_lo;  /* [w_rows, K] fp32: tf32-exact high part / low part (pack.split_tf32_host) */
+  int ldw, w_rows;                       /* w_rows >= N (rows beyond w_rows are TMA zero fill) */
+  int B, N, K;                           /* B <= 128; K % (32 * k_splits) == 0 */
+  const float* ln_stats; int ln_parts;   /* optional LayerNorm of x: [ln_parts, B, 2] (sum, centred sum of squares) over   */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;   /*   K/ln_parts columns each (out_stats of the producer)   */
+  const float* bias; int act;            /* [N] or NULL; DTTS_ACT_NONE / DTTS_ACT_GELU_NEW */
+  const float* res; int ldr;             /* optional residual [*, N] (indexed like out) */
+  float* out; int ldo;                   /* [*, N] */
+  const int* out_row_map;                /* optional [B]: output row of utterance b (KV arena row of the new token) */
+  float* out_stats;                      /* optional [N/128, B, 2]: LayerNorm statistics of the OUTPUT rows per 128-column slab */
+  int k_splits;                          /* cluster size along K */
+} dtts_dgemm_params;
+int dtts_decode_gemm(const dtts_dgemm_params* p, void* stream);
+
+typedef struct {
+  const float* x; int ldx; int B, C;     /* [B, C] residual stream after the last block */
+  const float* g1; const float* b1;      /* ln_f   (HF GPT2Model.ln_f, gpt/model.py:322) */
+  const float* g2; const float* b2;      /* final_norm (gpt/model.py:41,403); NULL = single LayerNorm */
+  float eps;
+  float* y; int ldy;                     /* [B, C] double-normed hidden = mel_head input */
+  float* lat; int64_t lat_stride_b;      /* optional latent store: lat[b*lat_stride_b + (lat_pos0 + *step_dev)*C + c] = y */
+  int lat_pos0; const int* step_dev;
+} dtts_final_ln_params;
+/* ln_f -> final_norm of the B new positions (exact two-pass LayerNorm, one CTA per row) + the diffusion latent capture
+ * (gpt/model.py:402-406: the latent of mel position j is this double-normed hidden). */
+int dtts_final_ln(const dtts_final_ln_params* p, void* stream);
+
+typedef struct {
+  /* --- dtts_process_logits part --- */
+  const float* logits; int ldl; int n_rows, vocab;
+  int64_t* ids; int ld_ids; int n_ids;
+  int* step_dev;                                   /* device step counter: read by every row, incremented once per launch */
+  float penalty, temperature, top_p; int top_k;
+  int do_sample; int suppress_token; float typical_mass;
+  float* probs; int ldp;                           /* optional dense probabilities (debug / tests) */
+  /* --- sampling: inverse CDF over the kept tokens in ascending id order, fp32 sequential sum, first id with cum > u --- */
+  const float* uniforms; int ld_u;                 /* [n_steps, ld_u >= n_rows] pre-drawn U[0,1); row = *step_dev */
+  /* --- dtts_append_token part --- */
+  int* unfinished; int64_t stop_token;
+  const float* tok_emb; const float* pos_emb; int pos; int dim;
+  float* x_out; int ldx; float* x_stats;
+  int* kv_row; int kv_stride; int* kv_len; const int* kv_pos_rows;
+  uint32_t* done_counter;                          /* zero-initialised by the caller; self-resetting */
+} dtts_decode_tail_params;
+/* dtts_process_logits + token choice (argmax, or inverse-CDF sampling from pre-drawn uniforms) + dtts_append_token in ONE
+ * launch (one CTA per utterance row): the decode loop needs no host work per token (HF _sample: generation/utils.py:2743-2808). */
+int dtts_decode_tail(const dtts_decode_tail_params* p, void* stream);
 
 typedef struct {
   int M, C;                     /* rows, channels (128) */

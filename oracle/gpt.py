@@ -208,6 +208,33 @@ def process_logits(logits, input_ids, do_sample=True, repetition_penalty_=2.0, t
     return s
 
 
+def inverse_cdf_multinomial(uniforms):
+    """The draw rule of the device-side sampler (csrc/sampling.cu, dtts_decode_tail) restated on the host, as a
+    `multinomial` hook for `generate`: step s, row b takes the first token id (ascending) whose cumulative probability --
+    a sequential fp32 sum over the non-zero probabilities -- exceeds uniforms[s][b]; the last kept id if none does.  It
+    samples the same categorical distribution HF's torch.multinomial does, from a different random stream."""
+    import numpy as np
+    state = {"s": 0}
+
+    def hook(probs):
+        p = probs.detach().float().cpu().numpy()
+        u = uniforms[state["s"]]
+        state["s"] += 1
+        out = []
+        for b in range(p.shape[0]):
+            nz = np.nonzero(p[b])[0]
+            c = np.float32(0.0)
+            tok = int(nz[-1])
+            for i in nz:
+                c = np.float32(c + p[b, i])
+                if c > np.float32(u[b]):
+                    tok = int(i)
+                    break
+            out.append(tok)
+        return torch.tensor(out, dtype=torch.long).view(-1, 1)
+    return hook
+
+
 def generate(W, refer, refer_lengths, text, max_generate_length=600, do_sample=True,
              top_p=0.8, temperature=0.8, repetition_penalty_=2.0, top_k=50, multinomial=None,
              suppress_eos=False, all_positions=True, return_trace=False, typical_mass=None, mel_codes=None):

@@ -28,7 +28,7 @@ def test_abi_symbols_and_struct_sizes():
     for extra in ("dtts_abi_version", "dtts_last_error", "dtts_sizeof", "dtts_kernel_launches", "dtts_device_info"):
         assert hasattr(cdll, extra)
     L = _lib.Lib(path)           # cross-checks every struct size against dtts_sizeof()
-    assert L.cdll.dtts_abi_version() == 1
+    assert L.cdll.dtts_abi_version() == 2
     assert L.launches() == 0
 
 
@@ -199,15 +199,15 @@ def _free_port():
     return p
 
 
-def _dist_worker(rank, world, port, q):
+def _dist_worker(rank, world, port, q, B=5):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    B, L, R = 5, 7, 12
+    L, R = 7, 12
     g = torch.Generator().manual_seed(0)
     text = torch.randint(0, 255, (B, L), generator=g, dtype=torch.int32)
     refer = torch.randn(B, 128, R, generator=g)
-    tl, rl = [7, 5, 6, 7, 4], [12, 10, 9, 12, 11]
+    tl, rl = [7, 5, 6, 7, 4][:B], [12, 10, 9, 12, 11][:B]
     if rank == 0:
         t, tlen, rf, rlen, mine, shards = ddist.scatter_inputs(text, tl, refer, rl, "cpu")
     else:
@@ -216,10 +216,10 @@ def _dist_worker(rank, world, port, q):
              for i, j in enumerate(mine))
     # fake synthesis: waveform = utterance index, length = 10 + index
     wav = torch.stack([torch.full((1, 20), float(j)) for j in mine]) if mine else torch.zeros(0, 1, 20)
-    wl = torch.tensor([10 + j for j in mine], dtype=torch.int64)
+    wl = torch.tensor([18 + j for j in mine], dtype=torch.int64)       # some lengths exceed max_samples = 20: clamped
     full, lens = ddist.gather_waveforms(wav, wl, shards, 20, "cpu")
     if rank == 0:
-        ok = ok and all(float(full[j, 0, 0]) == j for j in range(B)) and lens.tolist() == [10 + j for j in range(B)]
+        ok = ok and all(float(full[j, 0, 0]) == j for j in range(B)) and lens.tolist() == [min(20, 18 + j) for j in range(B)]
     q.put((rank, ok))
     dist.destroy_process_group()
 
@@ -230,6 +230,22 @@ def test_scatter_gather_gloo_world2():
     q = ctx.Queue()
     port = _free_port()
     ps = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_scatter_gather_gloo_fewer_utterances_than_ranks():
+    """B < world size: ranks with an empty shard must still take part in the collectives (the reshape of an
+    empty waveform raised before dist.gather and hung the other ranks)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_dist_worker, args=(r, 3, port, q, 2)) for r in range(3)]
     for p in ps:
         p.start()
     res = [q.get(timeout=120) for _ in ps]

@@ -44,12 +44,14 @@ def test_mel_style_encoder(model, golden, weights):
     assert relrms(out2[1], o2[0, :, 0]) < 3e-3
 
 
-@pytest.fixture(params=["persistent_step", "kernel_by_kernel_step"])
+@pytest.fixture(params=["persistent_step", "fused_step", "kernel_by_kernel_step"])
 def step_mode(request, model, monkeypatch):
-    """Both implementations of the decode step: the persistent cooperative kernel (batches <= 32, csrc/gpt_mega.cu) and
-    the kernel-by-kernel 3xTF32 step (the large-batch path), each with its own cached decode state."""
+    """All three implementations of the decode step: the persistent cooperative kernel (batches <= 32, csrc/gpt_mega.cu), the
+    fused tcgen05 step (csrc/gpt_dgemm.cu, 5..128 utterances: the bench path) and the kernel-by-kernel 3xTF32 step, each
+    with its own cached decode state."""
     import detail_tts_b200.gpt as G
     monkeypatch.setattr(G, "MEGA_MAX_B", 32 if request.param == "persistent_step" else 0)
+    monkeypatch.setattr(G, "FUSED_STEP", request.param == "fused_step")
     model.gpt._states.clear()
     yield request.param
     model.gpt._states.clear()
@@ -252,7 +254,7 @@ def test_infer_flowvae(model, golden):
         wav = model.infer_flowvae(mel[b:b + 1].to(DEV), torch.tensor([Fr]), None, randn_like=CPU_HOOKS["randn_like_zp"])
         e = rms(wav, fx["wav"][b:b + 1])
         print("infer_flowvae wav rms err", e)
-        assert e < 2e-4, e
+        assert e < 1e-4, e          # the stage-wise waveform budget (BASELINE.json north_star)
 
 
 def test_enc_p_ragged(model, golden, weights):
@@ -275,19 +277,84 @@ def test_enc_p_ragged(model, golden, weights):
     assert out[1, :, lens[1]:].abs().max().item() == 0
 
 
-def test_chain_b1(model, golden):
-    """Whole chain at B=1 with the reference's RNG order (golden 'chain' fixture)."""
-    fx = golden["chain"]
-    torch.manual_seed(fx["seed"])
+def _chain_vs_reference(model, weights, text, refer, R, G, seed, ref_codes, ref_mel, ref_wav, **kw):
+    """One utterance through the whole chain with the reference's RNG order; returns the error figures.  The stage-wise
+    waveform budget (1e-4) is asserted on the vocoder stage alone: the GPU waveform against the CPU oracle's fp32 flow-VAE +
+    vocoder fed with the SAME (GPU) mel and the same z_p noise.  The end-to-end figure additionally inherits the diffusion
+    stage's mel error through the vocoder's gain; it is reported (and recorded in DESIGN.md section 4), not hidden."""
+    import oracle.flowvae as of
+    drawn = {}
+
+    def zp_noise(x):
+        drawn["zp"] = torch.randn(x.shape)
+        return drawn["zp"]
+    hooks = dict(CPU_HOOKS, randn_like_zp=zp_noise)
+    torch.manual_seed(seed)
     tr = {}
-    wav, wl = model.infer_batch(fx["text"], [fx["text"].shape[1]], fx["refer"], fx["lengths"].tolist(),
-                                max_generate_length=fx["G"], hooks=CPU_HOOKS, trace=tr)
-    assert torch.equal(tr["codes"].cpu(), fx["codes"])
-    em = rms(tr["mel"], fx["mel"]) / (2.7 + 11.512925465) * 2     # in normalised-mel units
-    ew = rms(wav, fx["wav"])
-    print("chain mel rms (normalised)", em, "wav rms", ew)
-    assert em < 1e-3
-    assert ew < 1e-3   # end-to-end waveform inherits the mel error (stage-wise 1e-4 is tested above)
+    wav, wl = model.infer_batch(text, [text.shape[1]], refer, [R], max_generate_length=G, hooks=hooks, trace=tr, **kw)
+    assert torch.equal(tr["codes"].cpu(), ref_codes), (tr["codes"].cpu().tolist(), ref_codes.tolist())
+    em = rms(tr["mel"], ref_mel) / (2.7 + 11.512925465) * 2     # in normalised-mel units
+    ew = rms(wav, ref_wav)
+    F_ = ref_mel.shape[-1]
+    ow = of.infer_flowvae(weights, tr["mel"].cpu(), torch.tensor([F_]), randn_like=lambda m: drawn["zp"])
+    own, inherited = rms(wav, ow), rms(ow, ref_wav)
+    print(f"chain: mel rms (normalised) {em:.3e} | wav e2e {ew:.3e} = vocoder stage alone {own:.3e} (+) inherited from the mel "
+          f"error {inherited:.3e} | wav rms {float(ref_wav.pow(2).mean().sqrt()):.4f}")
+    return em, ew, own, inherited
+
+
+def test_chain_b1(model, golden, weights):
+    """Whole chain at B=1 with the reference's RNG order (golden 'chain' fixture, 6 codes)."""
+    fx = golden["chain"]
+    em, ew, own, inherited = _chain_vs_reference(model, weights, fx["text"], fx["refer"], int(fx["lengths"][0]), fx["G"], fx["seed"],
+                                                 fx["codes"], fx["mel"], fx["wav"])
+    assert em < 1e-3, em
+    assert own < 1e-4, own
+    assert ew < 2e-4, ew
+
+
+def test_config1_chain_on_1wav_prompt(model, weights):
+    """BASELINE config 1: the reference's own prompt 1.wav (R = 416 log-mel frames computed by the reference), the demo
+    sentence's 38 token ids, greedy decode (EOS suppressed: T = 70 codes = 2.99 s), diffusion seeded with config train.seed:
+    codes bit-exact, mel <= 1e-3 RMS, vocoder stage <= 1e-4 RMS against the unmodified reference (tests/golden/make_configs.py)."""
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_chain.pt"), map_location="cpu")
+    R = fx["refer"].shape[-1]
+    assert R == 416 and fx["codes"].shape == (1, 70)
+
+    # greedy tokens + the diffusion / z_p noise drawn from the CPU generator exactly as the reference run did
+    def run():
+        import oracle.flowvae as of
+        drawn = {}
+
+        def zp_noise(x):
+            drawn["zp"] = torch.randn(x.shape)
+            return drawn["zp"]
+        hooks = dict(CPU_HOOKS, randn_like_zp=zp_noise)
+        tr = {}
+        # the reference run seeded the generator AFTER the (greedy, RNG-free) GPT stage: seed inside the first noise hook
+        first = {"done": False}
+
+        def randn(shape):
+            if not first["done"]:
+                torch.manual_seed(fx["seed"])
+                first["done"] = True
+            return torch.randn(shape)
+        hooks["randn"] = randn
+        wav, wl = model.infer_batch(fx["text"], [fx["text"].shape[1]], fx["refer"], [R], max_generate_length=fx["G"],
+                                    do_sample=False, suppress_eos=True, hooks=hooks, trace=tr)
+        assert torch.equal(tr["codes"].cpu(), fx["codes"]), "greedy codes differ from the reference"
+        lat_err = relrms(tr["latent"], fx["latent"])
+        em = rms(tr["mel"], fx["mel"]) / (2.7 + 11.512925465) * 2
+        ew = rms(wav, fx["wav"])
+        ow = of.infer_flowvae(weights, tr["mel"].cpu(), torch.tensor([fx["mel"].shape[-1]]), randn_like=lambda m: drawn["zp"])
+        own, inherited = rms(wav, ow), rms(ow, fx["wav"])
+        print(f"config 1 (1.wav, T=70): latent rel {lat_err:.2e} | mel rms (normalised) {em:.3e} | wav e2e {ew:.3e} = vocoder stage "
+              f"alone {own:.3e} (+) inherited from the mel error {inherited:.3e}")
+        return lat_err, em, ew, own
+    lat_err, em, ew, own = run()
+    assert lat_err < 1e-4 and em < 1e-3 and own < 1e-4, (lat_err, em, own)
+    assert ew < 2e-4, ew
 
 
 def test_batch_equals_per_utterance(model):
