@@ -92,13 +92,38 @@ def gather_waveforms(wav, wav_lengths, shards, max_samples, device, dst=0):
     return full, lens
 
 
-def synthesize_sharded(model, text, text_lengths, refer, refer_lengths, max_samples, src=0, **infer_kw):
+def synthesize_sharded(model, text, text_lengths, refer, refer_lengths, max_samples, src=0, pipe=None, out=None, **infer_kw):
     """api.py-level entry for a multi-GPU box: rank `src` passes the whole batch (host or device
-    tensors), the others pass None.  Returns (wav, lengths) on rank `src`, (None, None) elsewhere."""
+    tensors), the others pass None.  Returns (wav, lengths) on rank `src`, (None, None) elsewhere.
+    `pipe` (model.SynthPipeline): the scatter + GPT stage run on the pipeline's first stream, the diffusion / vocoder stage and
+    the gather on its second one, so successive calls overlap; the returned tensors are then ready after `pipe.drain()`.
+    `out` (pinned host tensor, rank `src`): receives the gathered waveforms asynchronously."""
     dev = model.device
-    t, tl, rf, rl, mine, shards = scatter_inputs(text, text_lengths, refer, refer_lengths, dev, src)
+    if pipe is None:
+        t, tl, rf, rl, mine, shards = scatter_inputs(text, text_lengths, refer, refer_lengths, dev, src)
+        if len(mine):
+            wav, wl = model.infer_batch(t, tl.tolist(), rf, rl.tolist(), **infer_kw)
+        else:
+            wav, wl = torch.zeros(0, 1, 1, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)
+        full, lens = gather_waveforms(wav, wl, shards, max_samples, dev, dst=src)
+        if out is not None and full is not None:
+            out.copy_(full, non_blocking=True)
+        return full, lens
+    cur = torch.cuda.current_stream()
+    pipe.s_codes.wait_stream(cur)
+    with torch.cuda.stream(pipe.s_codes):
+        t, tl, rf, rl, mine, shards = scatter_inputs(text, text_lengths, refer, refer_lengths, dev, src)
+        tl, rl = tl.tolist(), rl.tolist()
     if len(mine):
-        wav, wl = model.infer_batch(t, tl.tolist(), rf, rl.tolist(), **infer_kw)
+        with torch.cuda.stream(pipe.s_codes):      # submit() makes its first stream wait for the "current" one
+            wav, wl = pipe.submit(t, tl, rf, rl, **infer_kw)
     else:
         wav, wl = torch.zeros(0, 1, 1, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)
-    return gather_waveforms(wav, wl, shards, max_samples, dev, dst=src)
+    with torch.cuda.stream(pipe.s_audio):
+        full, lens = gather_waveforms(wav, wl, shards, max_samples, dev, dst=src)
+        if out is not None and full is not None:
+            out.copy_(full, non_blocking=True)
+        if full is not None:
+            full.record_stream(cur)
+            lens.record_stream(cur)
+    return full, lens

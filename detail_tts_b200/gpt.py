@@ -40,7 +40,7 @@ FUSED_SPLITS = tuple(int(v) for v in os.environ.get("DTTS_GPT_FUSED_SPLITS", "4,
 
 
 def _i32(x, device):
-    return torch.tensor(x, dtype=torch.int32, device=device)
+    return ops.dev_tensor(x, torch.int32, device)
 
 
 class MelStyleEncoder:
@@ -424,7 +424,7 @@ class _DecodeState:
         self.step.zero_()
         if self.loop_plan is not None:
             self.done.zero_()
-        self.kv_base.copy_(torch.tensor([p + self.n_mel0 for p in P], dtype=torch.int32), non_blocking=False)
+        self.kv_base.copy_(ops.dev_tensor([p + self.n_mel0 for p in P], torch.int32, self.kv_base.device))
 
     def _run_plan_pdl(self, plan):
         """A plan's launches with programmatic dependent launch between them (see dtts_set_pdl)."""
@@ -491,6 +491,7 @@ class UnifiedVoice:
                                                     tf32x3=self.tf32x3 and os.environ.get("DTTS_COND_TF32X3", "1") != "0")
         self.max_mel_positions = self.mel_pos.shape[0]
         self.last_latents = None
+        self.min_kv_positions = 0       # lower bound on the KV arena rows per utterance (prefix + generated positions)
         self.last_uniforms = None       # [G, B] uniforms the in-graph sampler consumed in the last call (parity checks)
         self.last_lengths = None
         self.use_cuda_graph = True      # replay the ~95-launch decode step as one CUDA graph
@@ -548,7 +549,7 @@ class UnifiedVoice:
             ids += row
             pos += list(range(len(row)))
             dst += [seq_off[b] + 1 + i for i in range(len(row))]
-        ops.embed(torch.tensor(ids, dtype=torch.long, device=dev), self.text_embedding, x, pos_table=self.text_pos,
+        ops.embed(ops.dev_tensor(ids, torch.long, dev), self.text_embedding, x, pos_table=self.text_pos,
                   pos=_i32(pos, dev), dst_row=_i32(dst, dev))
         if mel_ids is not None:
             ids, pos, dst = [], [], []
@@ -558,7 +559,7 @@ class UnifiedVoice:
                 ids += row
                 pos += list(range(len(row)))
                 dst += [seq_off[b] + P[b] + i for i in range(len(row))]
-            ops.embed(torch.tensor(ids, dtype=torch.long, device=dev), self.mel_embedding, x, pos_table=self.mel_pos,
+            ops.embed(ops.dev_tensor(ids, torch.long, dev), self.mel_embedding, x, pos_table=self.mel_pos,
                       pos=_i32(pos, dev), dst_row=_i32(dst, dev))
         return x, seq_off, seq_len, P
 
@@ -706,7 +707,7 @@ class UnifiedVoice:
         y = self._trunk_rows(x, seq_off, seq_len, st.arena, st.stride)
 
         # first token: from the prefill's last position (the <start_mel> token) of every utterance
-        last_rows = torch.tensor([seq_off[b] + seq_len[b] - 1 for b in range(B)], dtype=torch.long, device=dev)
+        last_rows = ops.dev_tensor([seq_off[b] + seq_len[b] - 1 for b in range(B)], torch.long, dev)
         torch.index_select(y, 0, last_rows, out=st.t32)
         st.head_plan.run()
         st.latents[:, 0].copy_(st.hn)
@@ -771,6 +772,8 @@ class UnifiedVoice:
         # nothing): real traffic with varying text lengths reuses one state instead of re-recording and re-capturing the graph
         Pcap = -(-Pmax // 16) * 16
         Gcap = max(G, min(-(-G // 64) * 64, self.max_mel_positions - 1 - n_mel0))
+        if self.min_kv_positions:          # a fixed KV capacity per utterance (long-form serving: BASELINE config 5 sizes it 2048)
+            Gcap = max(Gcap, self.min_kv_positions - Pcap - n_mel0)
         key = (B, Pcap, Gcap, sampling, n_mel0)
         st = self._states.get(key)
         if st is not None:

@@ -10,7 +10,7 @@ import os
 
 import torch
 
-from . import synth
+from . import ops, synth
 from .diffusion import DiffusionTts, SpacedDiffusion, denormalize_torch_mel, do_spectrogram_diffusion, space_timesteps
 from .flowvae import FlowVAE
 from .gpt import STOP_MEL, UnifiedVoice
@@ -75,8 +75,6 @@ class SynthesizerTrn:
         pad), refer [B,128,Rmax] log-mel, refer_lengths [B].
         Returns (wav [B,1,1024*Tmax] zero beyond each utterance, wav_lengths [B] in samples).
         `hooks`: optional dict of RNG overrides {multinomial, randn, randn_like, randn_like_zp} (tests)."""
-        hooks = hooks or {}
-        dev = self.device
         marks = []
 
         def mark(name):
@@ -85,6 +83,18 @@ class SynthesizerTrn:
                 e.record()
                 marks.append((name, e))
         mark("start")
+        g = self._stage_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample, suppress_eos, hooks or {}, mark)
+        wav, wl = self._stage_audio(g, noise_scale, hooks or {}, mark, trace)
+        if trace is not None and marks:
+            torch.cuda.synchronize()
+            trace["stage_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+        return wav, wl
+
+    def _stage_codes(self, text, text_lengths, refer, refer_lengths, max_generate_length, do_sample, suppress_eos, hooks, mark):
+        """Stage 1 of `infer_batch`: GPT code tokens + the diffusion latents captured from the decode (model_24k.py:782-799).
+        Everything it returns is a fresh copy, so the next batch's stage 1 may start before this batch's stage 2 has run
+        (SynthPipeline)."""
+        dev = self.device
         codes, T, tl, rl, refer = self._generate_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample,
                                                        suppress_eos, hooks)
         mark("gpt")
@@ -92,26 +102,35 @@ class SynthesizerTrn:
         # for it (codes[:, :-1] is empty, model_24k.py:795-803 then fails inside the diffusion model).  Here it yields an empty
         # waveform (length 0) and the rest of the batch is synthesised as usual.
         keep = [b for b in range(len(T)) if T[b] >= 1]
-        B_all, T_all = len(T), T
+        g = dict(B_all=len(T), T_all=T, sel=None, codes=codes)
         if not keep:
-            if trace is not None:
-                trace.update(codes=codes, T=T_all)
-            return torch.zeros(B_all, 1, 0, device=dev), torch.zeros(B_all, dtype=torch.long, device=dev)
-        sel = None
-        if len(keep) < B_all:
-            sel = torch.tensor(keep, dtype=torch.long, device=dev)
-            T = [T_all[b] for b in keep]
+            return g
+        if len(keep) < len(T):
+            sel = g["sel"] = ops.dev_tensor(keep, torch.long, dev)
+            T = [T[b] for b in keep]
             tl, rl = [tl[b] for b in keep], [rl[b] for b in keep]
             text, refer, codes = text.to(dev)[sel], refer[sel], codes[sel]
         Tmax = max(T)
         codes = codes[:, :Tmax]
         if self.capture_latents:
-            latent = self.gpt.last_latents[:, :Tmax] if sel is None else self.gpt.last_latents[sel, :Tmax]
-            latent = latent.contiguous()
+            lat = self.gpt.last_latents[:, :Tmax] if g["sel"] is None else self.gpt.last_latents[g["sel"], :Tmax]
+            latent = lat.clone()
         else:
             latent = self.gpt.forward(refer, rl, text, tl, codes, None, return_latent=True, clip_inputs=False,
                                       mel_lengths=T)
         mark("latents")
+        g.update(T=T, rl=rl, refer=refer, codes=codes, latent=latent)
+        return g
+
+    def _stage_audio(self, g, noise_scale, hooks, mark, trace=None):
+        """Stage 2 of `infer_batch`: diffusion conditioning + 50 x 2-eval sampler + flow-VAE + vocoder (model_24k.py:802-808)."""
+        dev = self.device
+        B_all, T_all = g["B_all"], g["T_all"]
+        if "latent" not in g:              # every utterance stopped at its first token
+            if trace is not None:
+                trace.update(codes=g["codes"], T=T_all)
+            return torch.zeros(B_all, 1, 0, device=dev), torch.zeros(B_all, dtype=torch.long, device=dev)
+        T, rl, refer, latent, sel = g["T"], g["rl"], g["refer"], g["latent"], g["sel"]
         cond = self.diffusion.get_conditioning(refer, rl)                        # model_24k.py:802
         mark("diff_cond")
         mel = do_spectrogram_diffusion(self.diffusion, self.infer_diffuser, latent, cond, temperature=1.0,
@@ -126,13 +145,9 @@ class SynthesizerTrn:
             full = torch.zeros(B_all, 1, wav.shape[-1], dtype=wav.dtype, device=dev)
             full[sel] = wav
             wav = full
-            T = T_all
         if trace is not None:
-            trace.update(codes=codes, T=T, latent=latent, cond=cond, mel=mel)
-            if marks:
-                torch.cuda.synchronize()
-                trace["stage_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
-        return wav, torch.tensor([1024 * t for t in T], device=dev)
+            trace.update(codes=g["codes"], T=T_all, latent=latent, cond=cond, mel=mel)
+        return wav, ops.dev_tensor([1024 * t for t in T_all], torch.long, dev)
 
     @torch.no_grad()
     def infer(self, text, text_length, refer, refer_lengths, noise_scale=0.667, **kw):
@@ -193,3 +208,47 @@ def load_model(model_name, model_path, config_path=None, device="cuda", **kw):
         ckpt = torch.load(model_path, map_location="cpu")
         sd = ckpt["model"] if "model" in ckpt else ckpt["G"]
     return SynthesizerTrn(sd, device=device, **kw)
+
+
+class SynthPipeline:
+    """Two-stage software pipeline over successive batches: the latency-bound GPT decode of
+    batch i+1 (one small CUDA graph per token, most SMs idle) runs on its own high-priority stream while the tensor-bound
+    diffusion + vocoder stage of batch i runs on a second stream.  The stages only share read-only weights; what stage 1
+    hands over are fresh copies (codes, latents).  `submit` enqueues one batch and returns immediately after the GPT stage's
+    single host read (the per-utterance code counts); `drain` makes the caller's stream wait for everything submitted."""
+
+    def __init__(self, model):
+        self.model = model
+        self.s_codes = torch.cuda.Stream(device=model.device, priority=-1)
+        self.s_audio = torch.cuda.Stream(device=model.device)
+
+    @torch.no_grad()
+    def submit(self, text, text_lengths, refer, refer_lengths, noise_scale=0.667, max_generate_length=600, do_sample=True,
+               suppress_eos=False, hooks=None, out=None):
+        """-> (wav, wav_lengths): tensors whose contents are ready once `drain()` (or a wait on the audio stream) has passed.
+        `out` (optional pinned host tensor [B, 1, >= samples]) receives the waveforms asynchronously on the audio stream."""
+        m, hooks = self.model, hooks or {}
+        cur = torch.cuda.current_stream()
+        self.s_codes.wait_stream(cur)          # the inputs were produced on the caller's stream
+        nomark = lambda name: None  # noqa: E731
+        with torch.cuda.stream(self.s_codes):
+            g = m._stage_codes(text, text_lengths, refer, refer_lengths, max_generate_length, do_sample, suppress_eos, hooks, nomark)
+            for v in g.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(self.s_audio)
+            ev = torch.cuda.Event()
+            ev.record(self.s_codes)
+        self.s_audio.wait_event(ev)
+        with torch.cuda.stream(self.s_audio):
+            wav, wl = m._stage_audio(g, noise_scale, hooks, nomark)
+            if out is not None:
+                n = min(out.shape[-1], wav.shape[-1])
+                out[:wav.shape[0], :, :n].copy_(wav[:, :, :n], non_blocking=True)
+            wav.record_stream(cur)
+            wl.record_stream(cur)
+        return wav, wl
+
+    def drain(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.s_codes)
+        cur.wait_stream(self.s_audio)

@@ -12,6 +12,19 @@ from ._lib import (ACT_GELU_NEW, ACT_LOG_CLAMP, ACT_LRELU, ACT_MISH, ACT_NONE, A
                    BIAS_RELPOS_TABLE, BIAS_WINDOW_REL)
 
 
+_SYNC_H2D = __import__("os").environ.get("DTTS_SYNC_H2D", "0") != "0"     # debugging: the old synchronous small copies
+
+
+def dev_tensor(data, dtype, device):
+    """Small host list -> device tensor WITHOUT a stream synchronisation: torch.tensor(data, device=cuda) copies from pageable
+    memory and waits for the stream, which serialises the host with everything queued before it (it kept the two-stream
+    pipeline of model.SynthPipeline from overlapping); a pinned staging tensor + non_blocking copy does not."""
+    t = torch.tensor(data, dtype=dtype)
+    if torch.device(device).type != "cuda" or _SYNC_H2D:
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def _ld(t):
     assert t.dim() == 2 and t.stride(1) == 1, "rows tensors must be 2-D with unit channel stride"
     return t.stride(0)
@@ -214,8 +227,8 @@ class RowsLayout:
         self.M = (o + align - 1) // align * align
         self.max_len = max(self.lens) if self.lens else 0
         self.device = device
-        self.off = torch.tensor(offs, dtype=torch.int32, device=device)
-        self.len = torch.tensor(self.lens, dtype=torch.int32, device=device)
+        self.off = dev_tensor(offs, torch.int32, device)
+        self.len = dev_tensor(self.lens, torch.int32, device)
         self._row_utt = None
 
     @property

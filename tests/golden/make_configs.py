@@ -1,6 +1,6 @@
 """Golden fixtures at the BASELINE.json config shapes, from the UNMODIFIED reference (run in the build container):
 
-    python tests/golden/make_configs.py [cfg1] [cfg2]
+    python tests/golden/make_configs.py [cfg1] [cfg2] [cfg5]
 
 cfg2 (BASELINE config 2, "batch=32 synthetic 50-token texts, GPT decode only vs reference"):
     rows 0..7 of the B=32 job (bench.py's make_inputs(32): L=50 text ids, 300-frame prompt), EOS suppressed,
@@ -113,7 +113,8 @@ def cfg1(model, W):
     R = refer.shape[-1]
     print("  1.wav ->", tuple(wav24.shape), "log-mel", tuple(refer.shape))
     ids = json.load(open(os.path.join(HERE, "tokenizer_kat.json")))["ids"]
-    text = torch.nn.functional.pad(torch.tensor([ids], dtype=torch.int32), (0, 1))  # api.py:24-25
+    assert len(ids) == 39 and ids[-1] == 0                                          # the fixture already carries api.py's pad
+    text = torch.nn.functional.pad(torch.tensor([ids[:-1]], dtype=torch.int32), (0, 1))  # api.py:24-25 -> [1, 39], P = 42
     rl = torch.tensor([R])
     G = T_CODES + 1
     codes = model.gpt.inference_speech_tortoise(refer, rl, text, do_sample=False, num_return_sequences=1,
@@ -145,6 +146,42 @@ def cfg1(model, W):
     print(f"wrote {out} ({os.path.getsize(out) / 1e6:.2f} MB) in {time.time() - t0:.0f}s")
 
 
+
+
+def cfg5(model, W):
+    """BASELINE config 5 ("long-form 60-sec chunked synthesis, KV-cache 2048"): ONE chunk of the long-form harness at its full
+    size -- 469 codes (20.0 s; a 60-s utterance = 3 such chunks, detail_tts_b200/longform.py), 120 text ids, 300-frame prompt --
+    through the unmodified reference: sampled codes (torch.manual_seed(5), EOS suppressed), latents, 50 x 2-eval diffusion
+    (F = 1876 frames), flow-VAE + vocoder.  -> tests/golden/cfg5_chunk.pt"""
+    t0 = time.time()
+    from vqvae.model_24k import do_spectrogram_diffusion
+    L, R, T = 120, 300, 469
+    text, refer = bench_inputs(1, L=L, R=R, seed=60)
+    rl = torch.tensor([R])
+    G = T + 1
+    torch.manual_seed(5)
+    codes = model.gpt.inference_speech_tortoise(refer, rl, text, do_sample=True, top_p=0.8, temperature=0.8, length_penalty=1.0,
+                                                num_return_sequences=1, repetition_penalty=2.0, max_generate_length=G,
+                                                suppress_tokens=[8193])
+    print(f"  reference GPT done {time.time() - t0:.0f}s", codes.shape)
+    torch.manual_seed(5)
+    o_codes = ogpt.generate(W, refer, rl, text, max_generate_length=G, do_sample=True, suppress_eos=True, all_positions=False)
+    assert torch.equal(codes, o_codes), ("cfg5 sampled: oracle diverges at", first_divergence(codes, o_codes))
+    c = codes[:, :-1]
+    lat = model.gpt(refer, rl, text, torch.tensor([text.shape[1]]), c.clone(), torch.tensor([T * 1024]), return_latent=True,
+                    clip_inputs=False)
+    cl = model.diffusion.get_conditioning(refer)
+    torch.manual_seed(6)
+    mel_n = do_spectrogram_diffusion(model.diffusion, model.infer_diffuser, lat, cl, temperature=1.0, verbose=False)
+    mel = odiff.denormalize_mel(mel_n)
+    wav = model.infer_flowvae(mel, torch.tensor([mel.shape[-1]]), None)
+    print(f"  reference chain done {time.time() - t0:.0f}s: mel {tuple(mel.shape)} wav {tuple(wav.shape)}")
+    fx = dict(L=L, R=R, input_seed=60, G=G, gpt_seed=5, noise_seed=6, codes=c, latent=lat.half(), mel=mel, wav=wav)
+    out = os.path.join(HERE, "cfg5_chunk.pt")
+    torch.save(fx, out)
+    print(f"wrote {out} ({os.path.getsize(out) / 1e6:.2f} MB) in {time.time() - t0:.0f}s")
+
+
 def main():
     which = sys.argv[1:] or ["cfg1", "cfg2"]
     model, cfg = refshim.build_reference_model()
@@ -155,6 +192,8 @@ def main():
         cfg1(model, sd)
     if "cfg2" in which:
         cfg2(model, sd)
+    if "cfg5" in which:
+        cfg5(model, sd)
 
 
 if __name__ == "__main__":

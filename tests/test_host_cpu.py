@@ -311,3 +311,52 @@ def test_sinc_resample_kernel_matches_oracle_definition():
     ref = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), (t * math.pi).sin() / (t * math.pi)) \
         * torch.cos(t * math.pi / 12) ** 2 * (80 * 0.99 / 147)
     assert (torch.from_numpy(k).double() - ref).abs().max() < 1e-7
+
+
+REF_TOK = "/root/reference/bpe_tokenizers"
+
+
+def test_text_frontend_pad_ids_and_punctuation():
+    """api.py:21-25 batching semantics: every row carries the trailing pad id 0 and its length counts it."""
+    from detail_tts_b200 import text as T
+    ids, lens = T.pad_ids([[5, 6, 7], [9], [1, 2, 3, 4, 5]])
+    assert ids.dtype == torch.int32 and ids.shape == (3, 6) and lens == [4, 2, 6]
+    assert ids[0].tolist() == [5, 6, 7, 0, 0, 0] and ids[2].tolist() == [1, 2, 3, 4, 5, 0]
+    assert T.remove_extraneous_punctuation("{a}[b]`c—d") == "(a)(b)'c-d"
+    assert T.remove_extraneous_punctuation("@") == "" and T.remove_extraneous_punctuation("a@b") == "a@b"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TOK + "/zh_tokenizer.json"), reason="reference tokenizer vocabularies not on this box")
+def test_text_frontend_matches_reference_tokenizer():
+    """detail_tts_b200.text against (a) the reference's only known-answer vector (demo.ipynb ids) and (b) the 128 mixed zh / en
+    sentences of BASELINE config 4 tokenised by the reference's own VoiceBpeTokenizer (tests/golden/make_cfg4.py), batched."""
+    import json
+    from detail_tts_b200 import text as T
+    here = os.path.dirname(os.path.abspath(__file__))
+    kat = json.load(open(os.path.join(here, "golden", "tokenizer_kat.json")))
+    zh = T.VoiceBpeTokenizer(REF_TOK + "/zh_tokenizer.json")
+    assert zh.encode(kat["text"]) == kat["ids"][:-1]            # the fixture's last id is api.py's pad
+    ids, lens = zh.encode_batch([kat["text"].strip()])
+    assert ids[0].tolist() == kat["ids"] and lens == [len(kat["ids"])]
+    assert zh.decode(torch.tensor(kat["ids"][:-1])).strip() == kat["text"].strip()
+    fx = json.load(open(os.path.join(here, "golden", "cfg4_mixed.json")))["items"]
+    mt = T.MixedTokenizer({"zh": REF_TOK + "/zh_tokenizer.json", "en": REF_TOK + "/en_tokenizer.json"})
+    ids, lens = mt.encode_batch([it["text"] for it in fx], [it["lang"] for it in fx], wrap_spaces=False)
+    assert ids.shape[0] == 128 and min(lens) >= 31 and max(lens) <= 71
+    for b, it in enumerate(fx):
+        assert ids[b, :lens[b] - 1].tolist() == it["ids"] and int(ids[b, lens[b] - 1:].abs().sum()) == 0
+
+
+def test_longform_chunker():
+    """detail_tts_b200.longform: chunks keep every token in order, respect the token budget derived from the reference's
+    600-code generation cap (vqvae/model_24k.py:792) and end on [SPACE] boundaries when one is near."""
+    import random
+    from detail_tts_b200.longform import plan_chunks, split_tokens
+    rng = random.Random(0)
+    for n, mt in ((360, 150), (100, 150), (151, 150), (1000, 171), (37, 5), (1, 1)):
+        ids = [(2 if rng.random() < 0.3 else rng.randint(3, 254)) for _ in range(n)]
+        ch = split_tokens(ids, mt)
+        assert sum(ch, []) == ids and all(0 < len(c) <= mt for c in ch) and len(ch) == -(-n // mt)
+    assert split_tokens([3, 4, 5, 6, 2, 7, 8, 9, 10, 11, 12], 7) == [[3, 4, 5, 6, 2], [7, 8, 9, 10, 11, 12]]   # ends on the [SPACE]
+    rows, owner = plan_chunks([[5] * 360, [6] * 100], max_codes=600, codes_per_token=4.0)
+    assert [len(r) for r in rows] == [120, 120, 120, 100] and owner == [0, 0, 0, 1]

@@ -83,8 +83,9 @@ def test_vocoder_long(model, weights):
 
 
 def test_gpt_decode_long_kv(model, weights):
-    """KV-cache decode over a long generation (300 codes, EOS suppressed): latents captured from the decode steps equal
-    the full second pass (gpt/model.py:429-491) -- exercises the arena at ~360 positions."""
+    """KV-cache decode over a long generation (300 codes, EOS suppressed; arena at ~360 positions): the latents captured from
+    the decode steps equal the ORACLE's second pass (UnifiedVoice.forward(return_latent=True), gpt/model.py:429-491, on the
+    same codes) and the repo's own second pass."""
     g = torch.Generator().manual_seed(11)
     text = torch.nn.functional.pad(torch.randint(3, 255, (2, 50), generator=g, dtype=torch.int32), (0, 1))
     refer = (torch.randn(2, 128, 200, generator=g) * 2 - 5).clamp(-11.5, 2.7)
@@ -93,5 +94,10 @@ def test_gpt_decode_long_kv(model, weights):
     assert codes.shape == (2, 301) and int(codes.max()) < 8193
     T = 300
     cap = model.gpt.last_latents[:, :T].clone()
+    import oracle.gpt as og
+    olat = og.latents(weights, refer, torch.tensor([200, 200]), text, codes[:, :T].cpu())
+    e = relrms(cap, olat)
+    print("long decode: captured latents vs oracle second pass, rel rms", e)
+    assert e < 1e-4, e
     lat = model.gpt.forward(refer.to(DEV), [200, 200], text, None, codes[:, :T], None, return_latent=True, clip_inputs=False)
-    assert relrms(cap, lat) < 1e-4, relrms(cap, lat)
+    assert relrms(lat, olat) < 1e-4, relrms(lat, olat)
