@@ -378,7 +378,10 @@ def main():
     ap.add_argument("--utts", type=int, default=N_UTT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="one step at a time (no overlap of step i+1's GPT decode with step i's diffusion)")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="overlap step i+1's GPT decode with step i's diffusion + vocoder on two CUDA streams (model.SynthPipeline). Off by default: "
+                         "+2.5 % at 1 GPU / +5 % on a 16-utterance shard, but 3 of 17 two-GPU runs died with an unspecified launch failure "
+                         "(never seen without the overlap, 0 of 8; nor at one GPU)")
     ap.add_argument("--config", default="b128", choices=["b128", "b64", "mixed128", "long60", "decode32"],
                     help="b128 = the headline job (BASELINE.json metric); the others are BASELINE.json's configs 3 / 4 / 5 / 2")
     args = ap.parse_args()
@@ -499,7 +502,7 @@ def main():
         return float(t[0]), float(t[1]), int(t[2]), clocks
 
     from detail_tts_b200.model import SynthPipeline
-    pipe = None if args.no_pipeline else SynthPipeline(model)
+    pipe = SynthPipeline(model) if args.pipeline else None
 
     def timed_pipelined(steps, warmup, sampler=None):
         """K steps back to back through the two-stream pipeline (the GPT decode of step i+1 overlaps the diffusion + vocoder of

@@ -215,7 +215,11 @@ class SynthPipeline:
     batch i+1 (one small CUDA graph per token, most SMs idle) runs on its own high-priority stream while the tensor-bound
     diffusion + vocoder stage of batch i runs on a second stream.  The stages only share read-only weights; what stage 1
     hands over are fresh copies (codes, latents).  `submit` enqueues one batch and returns immediately after the GPT stage's
-    single host read (the per-utterance code counts); `drain` makes the caller's stream wait for everything submitted."""
+    single host read (the per-utterance code counts); `drain` makes the caller's stream wait for everything submitted.
+    EXPERIMENTAL (measured on B200: 958 -> 936 ms per 128-utterance step, 187 -> 176 ms per 16-utterance shard; the two stages
+    time-slice the SMs at kernel granularity rather than truly sharing them): under the 2-process torchrun bench 3 of 17 runs
+    with the overlap ended in `unspecified launch failure`, none of 8 without it and none at one GPU -- not root-caused, so
+    bench.py keeps it opt-in (--pipeline)."""
 
     def __init__(self, model):
         self.model = model
