@@ -273,6 +273,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const bool gn = GN && lean && epi.gn_stats != nullptr;     // GN = false instantiations carry none of the statistics code
       const int gn_groups = gn ? epi.N / epi.gn_cpg : 0;
+      // Residual rows of this warp's first 32-column chunk: they do not depend on the accumulator, so they are requested
+      // BEFORE waiting for the MMAs (their HBM latency hides behind the main loop); inside the chunk loop the next chunk's
+      // residual is requested before the current chunk is processed.  (The 1x1 + residual convs are HBM-bound: with the loads
+      // issued chunk by chunk after the accumulator was ready the epilogue ran at ~18 GB/s per SM, 162 us vs 86 us at HBM peak.)
+      const bool res_pf = lean && epi.res != nullptr && !(WIDE_OK && wide16);
+      float4 rs_cur[8];
+      auto load_res = [&](int c, float4 (&rs)[8]) {
+        const int nn = n0 + c * 32 + cc;
+        const bool ok = c < BN / 32 && nn < epi.N;
+        const float* rp = epi.res + (size_t)mrow * epi.ldr + nn;
+        const size_t rstep = (size_t)4 * epi.ldr;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && ((vmask >> it) & 1u)) rs[it] = *reinterpret_cast<const float4*>(rp);
+          rp += rstep;
+        }
+      };
+      if (res_pf) load_res(cpar, rs_cur);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (WIDE_OK && wide16 && debug != 1) {
@@ -350,17 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n < epi.N) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
-            float4 rs[8];
-            if (epi.res) {
-              const float* rp = epi.res + (size_t)mrow * epi.ldr + n;
-              const size_t rstep = (size_t)4 * epi.ldr;
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((vmask >> it) & 1u) rs[it] = *reinterpret_cast<const float4*>(rp);
-                rp += rstep;
-              }
-            }
+            float4 (&rs)[8] = rs_cur;            // requested before the accumulator wait (first chunk) / right after the previous chunk
             float* o32 = epi.out_f32 ? epi.out_f32 + (size_t)mrow * epi.ldo32 + n : nullptr;
             __half* o16 = epi.out_f16 ? epi.out_f16 + (size_t)mrow * epi.ldo16 + n : nullptr;
             const size_t s32 = (size_t)4 * epi.ldo32, s16 = (size_t)4 * epi.ldo16;
@@ -396,6 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (o32) o32 += s32;
               if (o16) o16 += s16;
             }
+            if (epi.res) load_res(c + 2, rs_cur);   // next chunk of this warp: in flight during its tcgen05.ld + transpose
             if (gn) gn_accumulate(epi.gn_stats, gn_groups, n / epi.gn_cpg, uid, ps, pss, lane);
           }
         } else {
