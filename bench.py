@@ -357,9 +357,9 @@ def gemm_roofline(model, lib, pk):
     peak = pk["bf16_tflops_sustained"]
     # DRAM bytes per launch of the same 62 launches from the committed ncu capture (never measured live under a profiler)
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_G_gemm_traffic.json")))
-        if tj["launches"] == len(ms):
+    try:     # the capture is of the 128-utterance eval (71 938 rows incl. separators): only quoted for that shape
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")))
+        if tj["launches"] == len(ms) and eng.lay.M == 71938:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
