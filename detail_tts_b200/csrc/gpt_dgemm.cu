@@ -526,7 +526,10 @@ final_ln_kernel(const dtts_final_ln_params p) {
     }
   }
   float* lat = nullptr;
-  if (p.lat) lat = p.lat + (size_t)b * p.lat_stride_b + (size_t)(p.lat_pos0 + (p.step_dev ? *p.step_dev : 0)) * p.C;
+  if (p.lat) {
+    const int pos = p.lat_pos0 + (p.step_dev ? *p.step_dev : 0) - (p.row_step0 ? p.row_step0[b] : 0);
+    if (p.lat_T <= 0 || (pos >= 0 && pos < p.lat_T)) lat = p.lat + (size_t)b * p.lat_stride_b + (size_t)pos * p.C;
+  }
 #pragma unroll
   for (int i = 0; i < FL_MAXE; ++i) {
     const int c = tid + i * FL_THREADS;

@@ -65,7 +65,18 @@ process_logits_kernel(const dtts_decode_tail_params p, int64_t* argmax_out) {
   for (int i = tid; i < 512; i += PL_THREADS) bitmap[i] = 0;
   __syncthreads();
   // repetition penalty: every distinct id of the history is penalised once (gather/scatter semantics)
-  const int step = p.step_dev ? *p.step_dev : 0;
+  const int gstep = p.step_dev ? *p.step_dev : 0;                        // global step (uniform row)
+  const int step = gstep - (TAIL && p.row_step0 ? p.row_step0[row] : 0);  // this row's own step (continuous batching)
+  const bool frozen = TAIL && p.row_step0 && !p.unfinished[row];         // finished slot waiting to be harvested / rebound
+  if (frozen) {
+    // nothing of this row may change any more; still take part in the step-counter handshake
+    if (tid == 0 && p.done_counter) {
+      __threadfence();
+      const unsigned prev = atomicAdd(p.done_counter, 1u);
+      if (prev == (unsigned)p.n_rows - 1u) { *p.done_counter = 0u; *p.step_dev = gstep + 1; }
+    }
+    return;
+  }
   const int n_ids = p.n_ids + step;
   const int64_t* ids = p.ids + (long)row * p.ld_ids;
   for (int i = tid; i < n_ids; i += PL_THREADS) {
@@ -267,7 +278,7 @@ process_logits_kernel(const dtts_decode_tail_params p, int64_t* argmax_out) {
     }
     __syncthreads();
     if (tid == 0) {
-      const float u = p.uniforms[(long)step * p.ld_u + row];
+      const float u = p.uniforms[(long)gstep * p.ld_u + row];
       float c = 0.f;
       int tok = si[nk - 1];
       for (int i = 0; i < nk; ++i) {
@@ -288,7 +299,7 @@ process_logits_kernel(const dtts_decode_tail_params p, int64_t* argmax_out) {
     const int unf = p.unfinished[row];
     if (!unf) tok = p.stop_token;
     p.ids[(long)row * p.ld_ids + p.n_ids + step] = tok;
-    p.unfinished[row] = unf && (tok != p.stop_token);
+    p.unfinished[row] = unf && (tok != p.stop_token) && !(p.max_new > 0 && step + 1 >= p.max_new);
     const int pos0 = p.kv_pos_rows ? p.kv_pos_rows[row] : 0;
     if (p.kv_row) p.kv_row[row] = row * p.kv_stride + pos0 + step;
     if (p.kv_len) p.kv_len[row] = pos0 + step + 1;
@@ -310,7 +321,7 @@ process_logits_kernel(const dtts_decode_tail_params p, int64_t* argmax_out) {
     const unsigned prev = atomicAdd(p.done_counter, 1u);
     if (prev == (unsigned)p.n_rows - 1u) {
       *p.done_counter = 0u;
-      if (p.step_dev) *p.step_dev = step + 1;
+      if (p.step_dev) *p.step_dev = gstep + 1;
     }
   }
 }

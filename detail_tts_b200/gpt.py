@@ -190,9 +190,14 @@ class _DecodeState:
     def arena_bytes(B, Pmax, G, n_mel0):
         return N_LAYERS * B * (Pmax + n_mel0 + G) * 3 * D_MODEL * 4
 
-    def __init__(self, gpt, B, Pmax, G, sampling, n_mel0=1):
+    def __init__(self, gpt, B, Pmax, G, sampling, n_mel0=1, continuous_rows=0):
         """n_mel0: mel tokens already in the sequence when decoding starts: 1 (<start_mel>) for
-        inference_speech_tortoise, 2 + len(mel_codes) for inference_speech_valle."""
+        inference_speech_tortoise, 2 + len(mel_codes) for inference_speech_valle.
+        continuous_rows > 0: slot-reuse decoding (inference_speech_continuous): rows carry their own step origin and that many
+        rows of pre-drawn uniforms are kept."""
+        self.continuous = continuous_rows > 0
+        self.row_step0 = torch.zeros(B, dtype=torch.int32, device=gpt.device) if self.continuous else None
+        self.uniform_rows = continuous_rows if self.continuous else G
         self.nbytes = self.arena_bytes(B, Pmax, G, n_mel0)
         do_sample, penalty, temperature, top_p, top_k, suppress_token, typical_mass = sampling
         self.gpt, self.B, self.G, self.n_mel0 = gpt, B, G, n_mel0
@@ -332,7 +337,7 @@ class _DecodeState:
         if gpt.tf32x3 and not self.mega and B <= 128:
             # device-side token choice for the kernel-by-kernel step too (more than FUSED_MAX_B utterances): dtts_decode_tail +
             # the split-K step + final_norm with latent capture + the swap-AB mel_head GEMM; no host work per token
-            self.uniforms = torch.zeros(G, B, dtype=torch.float32, device=dev)
+            self.uniforms = torch.zeros(self.uniform_rows, B, dtype=torch.float32, device=dev)
             self.done = torch.zeros(1, dtype=torch.int32, device=dev)
 
             def tail():
@@ -342,14 +347,14 @@ class _DecodeState:
                          uniforms=self.uniforms, ld_u=B, unfinished=self.unfinished, stop_token=STOP_MEL,
                          tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos, pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL,
                          x_stats=None, kv_row=kv_row, kv_stride=stride, kv_len=kv_len, kv_pos_rows=self.kv_base,
-                         done_counter=self.done)
+                         done_counter=self.done, row_step0=self.row_step0, max_new=G if self.continuous else 0)
             with lib.record() as self.tail_plan:
                 tail()
             with lib.record() as self.loop_plan:
                 tail()
                 self.loop_plan.calls.extend(self.plan.calls[:-3])        # the step up to ln_f (t32); its head is replaced below
                 self.loop_plan.keep.extend(self.plan.keep)
-                ops.final_ln(t32, gpt.final_norm, None, hn, lat=self.latents, lat_pos0=0, step_dev=self.step)
+                ops.final_ln(t32, gpt.final_norm, None, hn, lat=self.latents, lat_pos0=0, step_dev=self.step, row_step0=self.row_step0)
                 ops.decode_gemm(hn, gpt.mel_head, self.logits, B, k_splits=FUSED_SPLITS[4], N=VOCAB)
         self.graph = None
         self.eager_runs = 0
@@ -369,7 +374,7 @@ class _DecodeState:
         xs, hn, arena, kv_row, kv_len, k_off, stride = self.xs, self.hn, self.arena, self.kv_row, self.kv_len, self.k_off, self.stride
         self.att, self.u = att, u = e(B, D_MODEL), e(B, 4 * D_MODEL)
         self.st_a, self.st_b = st_a, st_b = torch.zeros(D_MODEL // 128, B, 2, device=dev), torch.zeros(D_MODEL // 128, B, 2, device=dev)
-        self.uniforms = torch.zeros(G, B, dtype=torch.float32, device=dev)
+        self.uniforms = torch.zeros(self.uniform_rows, B, dtype=torch.float32, device=dev)
         self.done = torch.zeros(1, dtype=torch.int32, device=dev)
         iota = torch.arange(B, dtype=torch.int32, device=dev)
         ones = torch.ones(B, dtype=torch.int32, device=dev)
@@ -385,7 +390,7 @@ class _DecodeState:
                 ops.decode_gemm(att, ly["proj"], xs, B, res=xs, out_stats=st_b, k_splits=S[1])
                 ops.decode_gemm(xs, ly["fc"], u, B, ln=ly["ln2"], ln_stats=st_b, act=ops.ACT_GELU_NEW, k_splits=S[2])
                 ops.decode_gemm(u, ly["out"], xs, B, res=xs, out_stats=st_a, k_splits=S[3])
-            ops.final_ln(xs, T.ln_f, gpt.final_norm, hn, lat=self.latents, lat_pos0=0, step_dev=self.step)
+            ops.final_ln(xs, T.ln_f, gpt.final_norm, hn, lat=self.latents, lat_pos0=0, step_dev=self.step, row_step0=self.row_step0)
             ops.decode_gemm(hn, gpt.mel_head, self.logits, B, k_splits=S[4], N=VOCAB)
 
         def tail():
@@ -395,7 +400,7 @@ class _DecodeState:
                      uniforms=self.uniforms, ld_u=B, unfinished=self.unfinished, stop_token=STOP_MEL,
                      tok_emb=gpt.mel_embedding, pos_emb=gpt.mel_pos, pos=n_mel0, dim=D_MODEL, x_out=xs, ldx=D_MODEL,
                      x_stats=st_a, kv_row=kv_row, kv_stride=stride, kv_len=kv_len, kv_pos_rows=self.kv_base,
-                     done_counter=self.done)
+                     done_counter=self.done, row_step0=self.row_step0, max_new=G if self.continuous else 0)
 
         with lib.record() as self.plan:
             step()
@@ -424,6 +429,8 @@ class _DecodeState:
         self.step.zero_()
         if self.loop_plan is not None:
             self.done.zero_()
+        if self.continuous:
+            self.row_step0.zero_()
         self.kv_base.copy_(ops.dev_tensor([p + self.n_mel0 for p in P], torch.int32, self.kv_base.device))
 
     def _run_plan_pdl(self, plan):
@@ -563,7 +570,7 @@ class UnifiedVoice:
                       pos=_i32(pos, dev), dst_row=_i32(dst, dev))
         return x, seq_off, seq_len, P
 
-    def _trunk_rows(self, x, seq_off, seq_len, arena=None, arena_stride=0):
+    def _trunk_rows(self, x, seq_off, seq_len, arena=None, arena_stride=0, arena_slots=None):
         """All positions of every sequence through the 10 blocks + ln_f (causal attention).  With
         `arena` (list of per-layer [B*stride, 2304] buffers) the QKV rows are scattered into it so a
         decode loop can continue from them.  x is updated in place; returns ln_f(x) fp32."""
@@ -574,11 +581,12 @@ class UnifiedVoice:
         max_len = max(seq_len)
         row_map = None
         if arena is not None:
+            slots = list(range(B)) if arena_slots is None else [int(v) for v in arena_slots]   # arena slot of every sequence
             rm = []
             for b in range(B):
-                rm += [b * arena_stride + i for i in range(seq_len[b])]
+                rm += [slots[b] * arena_stride + i for i in range(seq_len[b])]
             row_map = _i32(rm, dev)
-            qoff = _i32([b * arena_stride for b in range(B)], dev)
+            qoff = _i32([slots[b] * arena_stride for b in range(B)], dev)
         if self.tf32x3:
             return self._trunk_rows_tf32(x, so, sl, max_len, arena, row_map, qoff if arena is not None else so)
         h = torch.empty(M, D_MODEL, dtype=dt, device=dev)
@@ -764,7 +772,7 @@ class UnifiedVoice:
         self.last_plan = st.plan
         return codes
 
-    def _decode_state(self, B, Pmax, G, sampling, n_mel0=1):
+    def _decode_state(self, B, Pmax, G, sampling, n_mel0=1, continuous_rows=0):
         """Persistent decode workspace (KV arena, step buffers, recorded launch plans, captured CUDA graph) for one
         (batch, prefix capacity, generation cap, sampling config): reused across calls, so the per-call cost is a
         few small resets instead of re-recording / re-capturing ~95 launches."""
@@ -774,7 +782,9 @@ class UnifiedVoice:
         Gcap = max(G, min(-(-G // 64) * 64, self.max_mel_positions - 1 - n_mel0))
         if self.min_kv_positions:          # a fixed KV capacity per utterance (long-form serving: BASELINE config 5 sizes it 2048)
             Gcap = max(Gcap, self.min_kv_positions - Pcap - n_mel0)
-        key = (B, Pcap, Gcap, sampling, n_mel0)
+        if continuous_rows:                # the generation cap is enforced on the device there: exact
+            Gcap = G
+        key = (B, Pcap, Gcap, sampling, n_mel0, continuous_rows)
         st = self._states.get(key)
         if st is not None:
             self._states.move_to_end(key)
@@ -783,10 +793,113 @@ class UnifiedVoice:
         budget = float(os.environ.get("DTTS_GPT_STATE_BYTES", 24e9))
         while self._states and sum(v.nbytes for v in self._states.values()) + need > budget:   # least recently used first
             self._states.popitem(last=False)
-        st = self._states[key] = _DecodeState(self, B, Pcap, Gcap, sampling, n_mel0)
+        st = self._states[key] = _DecodeState(self, B, Pcap, Gcap, sampling, n_mel0, continuous_rows)
         return st
 
     inference_speech = inference_speech_tortoise   # name used by the north star / gpt/model_deprect.py:528
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def inference_speech_continuous(self, speech_conditioning_latent, cond_lengths, text_inputs, text_lengths=None, slots=64,
+                                    max_generate_length=600, sync_every=8, typical_sampling=False, typical_mass=.9,
+                                    return_latents=True, **hf_generate_kwargs):
+        """Continuous batching of the decode: N utterances are decoded through `slots` <= 128
+        decode rows; a row whose utterance has emitted the stop token (or its max_generate_length-th token) is harvested and
+        REBOUND to the next waiting utterance -- its prefix is prefilled into the row's KV arena between two decode steps --
+        so short utterances do not hold a row until the longest one of a static batch ends (HF `_sample` pads them with 8193
+        instead, generation/utils.py:2797).  Every utterance is decoded exactly as `inference_speech_tortoise` decodes it at
+        B = 1 (same processors; tokens drawn in-graph by inverse CDF from pre-drawn uniforms).
+        Returns (codes: list of N int64 tensors [n_u] -- tokens up to and including the stop token, at most
+        max_generate_length --, latents: list of [n_u, 768] or None, log: per utterance (slot, first global step), and
+        self.last_uniforms = the [steps, slots] uniforms, for checking against the oracle)."""
+        kw = dict(hf_generate_kwargs)
+        do_sample = bool(kw.pop("do_sample", False))
+        top_p = float(kw.pop("top_p", 1.0))
+        temperature = float(kw.pop("temperature", 1.0))
+        top_k = int(kw.pop("top_k", 50))
+        penalty = float(kw.pop("repetition_penalty", 1.0))
+        kw.pop("length_penalty", None)
+        kw.pop("num_return_sequences", None)
+        if kw:
+            raise TypeError(f"unsupported generate kwargs: {sorted(kw)}")
+        dev = self.device
+        N = text_inputs.shape[0]
+        tl = self._text_lengths(text_inputs, text_lengths)
+        rl = [int(v) for v in cond_lengths]
+        G = int(max_generate_length)
+        S = min(int(slots), N, 128)
+        u_rows = (-(-N // S) + 1) * (G + sync_every) + sync_every        # upper bound on the global step count
+        sampling = (do_sample, penalty, temperature, top_p, top_k, -1, float(typical_mass) if typical_sampling else 0.0)
+        st = self._decode_state(S, max(tl) + 3, G, sampling, 1, continuous_rows=u_rows)
+        assert st.loop_plan is not None, "continuous batching needs the in-graph decode loop (more than MEGA_MAX_B rows)"
+        refer = speech_conditioning_latent.to(dev, torch.float32)
+        cond_all = self.get_conditioning(refer, rl)                               # [N, 768], one batch
+        start = torch.full((1, 1), START_MEL, dtype=torch.long, device=dev)
+        st.reset([tl[u] + 3 for u in range(S)], start.expand(S, 1))
+        st.uniforms.copy_(torch.rand(st.uniforms.shape, device=dev))
+        self.last_uniforms = st.uniforms
+        gstep = 0
+        slot_utt = [-1] * S
+        log = [None] * N
+        codes_out, lat_out = [None] * N, [None] * N
+
+        def bind(slot_list, utt_list):
+            """Prefill utterances `utt_list` into slots `slot_list`; their first-token logits go to st.logits[slot]."""
+            n = len(utt_list)
+            ui = torch.tensor(utt_list, dtype=torch.long, device=dev)
+            sl = ops.dev_tensor(slot_list, torch.long, dev)
+            tl_u = [tl[u] for u in utt_list]
+            x, seq_off, seq_len, P = self._build_sequences(cond_all[ui], text_inputs[ui.cpu()] if not text_inputs.is_cuda else text_inputs[ui],
+                                                           tl_u, start.expand(n, 1), [1] * n)
+            y = self._trunk_rows(x, seq_off, seq_len, st.arena, st.stride, arena_slots=slot_list)
+            last = ops.dev_tensor([seq_off[b] + seq_len[b] - 1 for b in range(n)], torch.long, dev)
+            t32 = y.index_select(0, last).contiguous()
+            hn = torch.empty_like(t32)
+            ops.final_ln(t32, self.final_norm, None, hn)
+            lg = torch.empty(n, st.logits.shape[1], dtype=torch.float32, device=dev)
+            ops.decode_gemm(hn, self.mel_head, lg, n, k_splits=FUSED_SPLITS[4], N=VOCAB)
+            st.logits.index_copy_(0, sl, lg)
+            st.latents[:, 0].index_copy_(0, sl, hn)
+            st.ids.index_fill_(0, sl, 1)
+            st.ids[:, st.n_ids0 - 1].index_fill_(0, sl, START_MEL)
+            st.unfinished.index_fill_(0, sl, 1)
+            st.kv_base.index_copy_(0, sl, ops.dev_tensor([p + 1 for p in P], torch.int32, dev))
+            st.row_step0.index_fill_(0, sl, gstep)
+            for s_, u in zip(slot_list, utt_list):
+                slot_utt[s_] = u
+                log[u] = (s_, gstep)
+
+        bind(list(range(S)), list(range(S)))
+        next_u = S
+        active = S
+        while active:
+            assert gstep + sync_every <= st.uniforms.shape[0], "continuous decode ran past its pre-drawn uniforms"
+            for _ in range(sync_every):
+                st.run_loop(self.use_cuda_graph)
+            gstep += sync_every
+            unf = st.unfinished.tolist()                                         # the one host read per sync_every tokens
+            done = [s_ for s_ in range(S) if slot_utt[s_] >= 0 and not unf[s_]]
+            if not done:
+                continue
+            ids_rows = st.ids[done, st.n_ids0:st.n_ids0 + G].cpu()
+            free = []
+            for j, s_ in enumerate(done):
+                u = slot_utt[s_]
+                row = ids_rows[j]
+                stop = (row == STOP_MEL).nonzero()
+                n_u = int(stop[0]) + 1 if len(stop) else G
+                codes_out[u] = row[:n_u].clone()
+                if return_latents:
+                    lat_out[u] = st.latents[s_, :n_u].clone()
+                slot_utt[s_] = -1
+                free.append(s_)
+            n_new = min(len(free), N - next_u)
+            if n_new:
+                bind(free[:n_new], list(range(next_u, next_u + n_new)))
+                next_u += n_new
+            active = sum(1 for s_ in range(S) if slot_utt[s_] >= 0)
+        self.last_plan = st.plan
+        return codes_out, (lat_out if return_latents else None), log
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -90,6 +90,42 @@ class SynthesizerTrn:
             trace["stage_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         return wav, wl
 
+    @torch.no_grad()
+    def infer_batch_continuous(self, text, text_lengths, refer, refer_lengths, slots=64, noise_scale=0.667, max_generate_length=600,
+                               do_sample=True, sync_every=8, trace=None):
+        """`infer_batch` whose GPT stage decodes the N utterances through `slots` reusable decode rows
+        (UnifiedVoice.inference_speech_continuous): with EOS live, utterances end at different steps and a finished row is
+        rebound to a waiting utterance instead of idling until the longest one ends.  Same return convention."""
+        dev = self.device
+        N = text.shape[0]
+        tl = [int(v) for v in text_lengths]
+        rl = [int(v) for v in refer_lengths]
+        refer = refer.to(dev, torch.float32)
+        kw = dict(do_sample=do_sample, repetition_penalty=2.0)
+        if do_sample:
+            kw.update(top_p=.8, temperature=.8, length_penalty=1.0)         # model_24k.py:786-791
+        codes_l, lat_l, log = self.gpt.inference_speech_continuous(refer, rl, text, text_lengths=tl, slots=slots,
+                                                                   max_generate_length=max_generate_length, sync_every=sync_every, **kw)
+        T_all = [int(c.numel()) - 1 for c in codes_l]                     # model_24k.py:795: codes[:, :-1]
+        keep = [u for u in range(N) if T_all[u] >= 1]
+        g = dict(B_all=N, T_all=T_all, sel=None)
+        Tmax = max([T_all[u] for u in keep], default=0)
+        codes = torch.full((N, max(Tmax, 1)), STOP_MEL, dtype=torch.long, device=dev)
+        for u in range(N):
+            codes[u, :T_all[u]] = codes_l[u][:T_all[u]].to(dev)
+        g["codes"] = codes
+        if keep:
+            latent = torch.zeros(len(keep), Tmax, 768, dtype=torch.float32, device=dev)
+            for j, u in enumerate(keep):
+                latent[j, :T_all[u]] = lat_l[u][:T_all[u]]
+            if len(keep) < N:
+                g["sel"] = ops.dev_tensor(keep, torch.long, dev)
+            g.update(T=[T_all[u] for u in keep], rl=[rl[u] for u in keep], refer=refer if len(keep) == N else refer[g["sel"]],
+                     codes=codes if len(keep) == N else codes[g["sel"]], latent=latent)
+        if trace is not None:
+            trace["decode_log"] = log
+        return self._stage_audio(g, noise_scale, {}, lambda name: None, trace)
+
     def _stage_codes(self, text, text_lengths, refer, refer_lengths, max_generate_length, do_sample, suppress_eos, hooks, mark):
         """Stage 1 of `infer_batch`: GPT code tokens + the diffusion latents captured from the decode (model_24k.py:782-799).
         Everything it returns is a fresh copy, so the next batch's stage 1 may start before this batch's stage 2 has run

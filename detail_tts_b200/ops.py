@@ -90,11 +90,12 @@ def decode_gemm(x, pw, out, B, ln=None, ln_stats=None, act=ACT_NONE, res=None, o
                     out_row_map=out_row_map, out_stats=out_stats, k_splits=k_splits)
 
 
-def final_ln(x, ln1, ln2, y, lat=None, lat_pos0=0, step_dev=None):
-    """ln_f -> final_norm of the B new rows (+ latent capture at position lat_pos0 + *step_dev of lat [B, T, C])."""
+def final_ln(x, ln1, ln2, y, lat=None, lat_pos0=0, step_dev=None, row_step0=None):
+    """ln_f -> final_norm of the B new rows (+ latent capture at position lat_pos0 + *step_dev [- row_step0[b]] of lat [B, T, C])."""
     _lib.lib().call("dtts_final_ln", x=x, ldx=_ld(x), B=x.shape[0], C=x.shape[1], g1=ln1[0], b1=ln1[1],
                     g2=ln2[0] if ln2 else None, b2=ln2[1] if ln2 else None, eps=1e-5, y=y, ldy=_ld(y), lat=lat,
-                    lat_stride_b=lat.stride(0) if lat is not None else 0, lat_pos0=lat_pos0, step_dev=step_dev)
+                    lat_stride_b=lat.stride(0) if lat is not None else 0, lat_pos0=lat_pos0, step_dev=step_dev,
+                    row_step0=row_step0, lat_T=lat.shape[1] if (lat is not None and row_step0 is not None) else 0)
 
 
 def split_tf32(x, hi, lo):

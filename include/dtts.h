@@ -260,6 +260,7 @@ typedef struct {
   float* y; int ldy;                     /* [B, C] double-normed hidden = mel_head input */
   float* lat; int64_t lat_stride_b;      /* optional latent store: lat[b*lat_stride_b + (lat_pos0 + *step_dev)*C + c] = y */
   int lat_pos0; const int* step_dev;
+  const int* row_step0; int lat_T;       /* continuous batching: row b's local step = *step_dev - row_step0[b]; positions >= lat_T (> 0) are not stored */
 } dtts_final_ln_params;
 /* ln_f -> final_norm of the B new positions (exact two-pass LayerNorm, one CTA per row) + the diffusion latent capture
  * (gpt/model.py:402-406: the latent of mel position j is this double-normed hidden). */
@@ -281,6 +282,11 @@ typedef struct {
   float* x_out; int ldx; float* x_stats;
   int* kv_row; int kv_stride; int* kv_len; const int* kv_pos_rows;
   uint32_t* done_counter;                          /* zero-initialised by the caller; self-resetting */
+  /* --- continuous batching (slot reuse): row b decodes its own utterance since global step row_step0[b]; its history
+   * column, mel position and KV row use the LOCAL step *step_dev - row_step0[b], the uniform row the global one.  A row is
+   * finished by the stop token or by its max_new-th token; a finished row is FROZEN (nothing of it is written any more: its
+   * codes / KV rows stay intact until the host harvests the slot and rebinds it to a waiting utterance). --- */
+  const int* row_step0; int max_new;
 } dtts_decode_tail_params;
 /* dtts_process_logits + token choice (argmax, or inverse-CDF sampling from pre-drawn uniforms) + dtts_append_token in ONE
  * launch (one CTA per utterance row): the decode loop needs no host work per token (HF _sample: generation/utils.py:2743-2808). */

@@ -271,3 +271,57 @@ def test_eos_rows_pad_like_hf_on_both_decode_paths(eos_weights, cfg2, dlib):
     assert torch.equal(dev_codes.cpu(), o_codes), first_divergence(dev_codes.cpu(), o_codes)
     host_codes = gpt.inference_speech_tortoise(refer.to(DEV), rl, text, multinomial=inv_cdf_hook(u), **kw)
     assert host_codes.shape == o_codes.shape and torch.equal(host_codes.cpu(), o_codes)
+
+
+def test_continuous_batching_equals_b1_runs(eos_weights, dlib):
+    """22 utterances (ragged text and prompt lengths) through 6 reusable decode rows, EOS live (rows stop at
+    different steps, finished rows are rebound to waiting utterances between decode steps).  Every utterance's tokens equal
+    the CPU oracle's B = 1 HF loop fed with the uniforms that utterance consumed (slot s, global steps step0, step0+1, ...);
+    the harvested latents equal the oracle's second pass."""
+    import bench
+    import oracle.gpt as og
+    from detail_tts_b200.gpt import UnifiedVoice
+    N, S, G = 22, 6, 20
+    g = torch.Generator().manual_seed(21)
+    tl = [int(v) for v in torch.randint(9, 22, (N,), generator=g)]
+    rl = [int(v) for v in torch.randint(40, 90, (N,), generator=g)]
+    text = torch.zeros(N, max(tl), dtype=torch.int32)
+    for u in range(N):
+        text[u, :tl[u] - 1] = torch.randint(3, 255, (tl[u] - 1,), generator=g, dtype=torch.int32)
+    refer = (torch.randn(N, 128, max(rl), generator=g) * 2 - 5).clamp(-11.5, 2.7)
+    gpt = UnifiedVoice(eos_weights, DEV)
+    torch.manual_seed(3)
+    codes, lats, log = gpt.inference_speech_continuous(refer.to(DEV), rl, text, text_lengths=tl, slots=S, max_generate_length=G,
+                                                       sync_every=4, repetition_penalty=2.0, **SAMPLING)
+    U = gpt.last_uniforms.cpu().numpy()
+    lens = [int(c.numel()) for c in codes]
+    print("continuous decode: tokens per utterance", lens, "| (slot, first step) per utterance", log)
+    assert len(set(lens)) > 2, "utterances were meant to end at different steps"
+    assert max(st0 for _, st0 in log) > 0, "no row was ever rebound"
+    for u in range(N):
+        slot, st0 = log[u]
+        useq = U[st0:st0 + G, slot:slot + 1]
+        o = og.generate(eos_weights, refer[u:u + 1, :, :rl[u]], torch.tensor([rl[u]]), text[u:u + 1, :tl[u]], max_generate_length=G,
+                        do_sample=True, multinomial=og.inverse_cdf_multinomial(useq), all_positions=False)
+        assert torch.equal(codes[u], o[0, :o.shape[1]].cpu()[:lens[u]]) and o.shape[1] == lens[u], (u, codes[u].tolist(), o.tolist())
+        if lens[u] > 1:
+            ol = og.latents(eos_weights, refer[u:u + 1, :, :rl[u]], torch.tensor([rl[u]]), text[u:u + 1, :tl[u]], codes[u][None, :lens[u] - 1])
+            e = float((lats[u][:lens[u] - 1].cpu() - ol[0]).pow(2).mean().sqrt() / ol.pow(2).mean().sqrt())
+            assert e < 1e-4, (u, e)
+
+
+def test_infer_batch_continuous_runs_whole_pipeline(eos_weights, dlib):
+    """The model-level entry: continuous decode -> batched diffusion / vocoder over the ragged code counts."""
+    from detail_tts_b200.model import SynthesizerTrn
+    import bench
+    model = SynthesizerTrn(eos_weights, device=DEV)
+    text, refer = bench.make_inputs(10, seed=9, L=12, R=60)
+    tr = {}
+    torch.manual_seed(2)
+    wav, wl = model.infer_batch_continuous(text, [13] * 10, refer, [60] * 10, slots=5, max_generate_length=14, sync_every=4, trace=tr)
+    T = tr["T"]
+    assert wav.shape[0] == 10 and wl.tolist() == [1024 * max(t, 0) for t in T] and bool(torch.isfinite(wav).all())
+    assert len(set(T)) > 1
+    for b in range(10):
+        assert T[b] == 0 or float(wav[b, :, :1024 * T[b]].abs().max()) > 0
+        assert float(wav[b, :, 1024 * max(T[b], 0):].abs().max() if wav.shape[-1] > 1024 * max(T[b], 0) else 0.0) == 0.0
