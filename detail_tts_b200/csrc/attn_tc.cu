@@ -219,6 +219,10 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (no-ops for a normal launch): everything above read only launch-invariant tables; q/k/v
+  // (written by the predecessor GEMM) are first touched below
+  pdl_launch();
+  pdl_wait();
 
   if (warp == W_TMA) {
     // ================================ TMA producer =================================
@@ -515,7 +519,10 @@ extern "C" int dtts_attention_f16_tc(const dtts_attention_params* p, void* strea
   const int qblocks = ceil_div(p->max_q_len, NT * BM);
   const long items = (long)p->n_utt * p->n_heads * qblocks;
   const int grid = items < g_sms ? (int)items : g_sms;
-  flash48_tc_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(mq, mk, mv, *p, qblocks);
+  {
+    cudaError_t le = launch_maybe_pdl(flash48_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem_bytes, (cudaStream_t)stream, mq, mk, mv, *p, qblocks);
+    if (le != cudaSuccess) DTTS_FAIL(-3, "flash48_tc launch failed: %s", cudaGetErrorString(le));
+  }
   DTTS_CHECK_LAUNCH("attention_f16_tc");
   return 0;
 }

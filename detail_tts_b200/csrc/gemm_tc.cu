@@ -148,10 +148,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CTAS == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (TF32) {   // GPT decode step: programmatic dependent launch (no-op otherwise); the prologue above overlapped the predecessor
-    pdl_launch();
-    pdl_wait();
-  }
+  // programmatic dependent launch (no-ops for a normal launch): the prologue above overlapped the predecessor's tail; nothing
+  // below reads memory the predecessor wrote before this wait (the decode step of the GPT and, round 2, the diffusion eval)
+  pdl_launch();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer =================================
@@ -502,11 +502,13 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_dtts_pdl ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2, GN>, ma, mw, ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
                                       kb_all, (long)0, g_debug);
   if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc pair launch failed: %s", cudaGetErrorString(le));
@@ -548,13 +550,10 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
     e.act = DTTS_ACT_NONE; e.act16 = DTTS_ACT_NONE; e.alpha = 1.0f; e.accumulate = 0; e.row_utt = nullptr;
   }
   dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
-  if (TF32) {
+  {
     cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32, 1, GN>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, e, p->K, p->taps,
                                       p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
     if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc launch failed: %s", cudaGetErrorString(le));
-  } else {
-    gemm_tc_kernel<BN, TF32, 1, GN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mw, ma2, mw2, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
-                                                                        kb_per, (long)p->split_stride, g_debug);
   }
   DTTS_CHECK_LAUNCH("gemm_tc");
   return 0;

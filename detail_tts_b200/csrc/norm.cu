@@ -556,6 +556,8 @@ constexpr int GNA_ROWS = 64;
 template <typename T>
 __global__ void __launch_bounds__(384, sizeof(T) == 4 ? 2 : 3)
 groupnorm_apply_kernel(const dtts_gn_apply_params p, const int rows_per_cta) {
+  pdl_launch();                                  // (programmatic dependent launch inside the diffusion eval graph; no-ops otherwise)
+  pdl_wait();
   const int C8 = p.C >> 3;                       // 8-channel vectors per row
   const int rl = blockDim.x / C8;                // row lanes
   const int col = threadIdx.x % C8, rlane = threadIdx.x / C8;
@@ -866,8 +868,8 @@ extern "C" int dtts_groupnorm_apply(const dtts_gn_apply_params* p, void* stream)
   int rows = GNA_ROWS;       // smaller row tiles while the grid would leave SMs (2-3 resident CTAs each) idle
   while (rows > 16 && ceil_div(p->M, rows) < 2 * 148 * (p->x_is_f16 ? 3 : 2)) rows >>= 1;
   const int grid = ceil_div(p->M, rows);
-  if (p->x_is_f16) groupnorm_apply_kernel<__half><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, rows);
-  else groupnorm_apply_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, rows);
+  if (p->x_is_f16) launch_maybe_pdl(groupnorm_apply_kernel<__half>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, *p, rows);
+  else launch_maybe_pdl(groupnorm_apply_kernel<float>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, *p, rows);
   DTTS_CHECK_LAUNCH("groupnorm_apply");
   return 0;
 }

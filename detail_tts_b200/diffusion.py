@@ -28,6 +28,12 @@ MODEL_CH, HEADS, IN_CH, OUT_CH = 768, 16, 128, 256
 FLASH_IMPL = os.environ.get("DTTS_FLASH", "tc")     # "tc": tcgen05 kernel (attn_tc.cu); "mma": mma.sync kernel (attn_flash.cu)
 FLASH_IMPL = True if FLASH_IMPL == "mma" else "tc"
 FUSE_GN_STATS = os.environ.get("DTTS_GN_FUSED", "1") != "0"   # GroupNorm statistics in the producing GEMM's epilogue
+# programmatic dependent launch between the kernels of one eval (gemm_tc / groupnorm_apply / flash48_tc call
+# griddepcontrol.launch_dependents + wait): the next kernel's prologue (barrier init, TMEM alloc, tensor-map prefetch) overlaps
+# the previous kernel's tail -- matters on small shards where the ~124 launches of an eval are 15-25 us each
+# Measured (B200): 16-utterance shard 181.7 -> 179.4 ms per step; at 128 utterances it LOSES (947 -> 974 ms: the next GEMM's CTAs
+# become resident early and spin, taking occupancy from the HBM-bound GroupNorm pass still running), hence the row limit.
+EVAL_PDL_MAX_ROWS = int(os.environ.get("DTTS_DIFF_PDL_ROWS", "20000"))
 ENGINE_CACHE = int(os.environ.get("DTTS_DIFF_ENGINES", "2"))      # fixed-buffer eval engines kept per batch layout (LRU)
 GRAPH_MAX_ROWS = int(os.environ.get("DTTS_DIFF_GRAPH_ROWS", "100000"))   # CUDA-graph the eval below this many rows (0 = never); measured at the 72 k-row bench shape: 954 vs 964 ms per step
 F16 = torch.float16
@@ -440,6 +446,14 @@ class _Engine:
             g.replay()
             plan.replayed()
             return self.out
+        cdll = ops._lib.lib().cdll
+        old_pdl = cdll.dtts_set_pdl(1 if self.lay.M <= EVAL_PDL_MAX_ROWS else 0)
+        try:
+            return self._eval_eager_and_capture(plan, per_utt)
+        finally:
+            cdll.dtts_set_pdl(old_pdl)
+
+    def _eval_eager_and_capture(self, plan, per_utt):
         plan.run()
         # Small shards (e.g. 16 utterances per GPU at N=8) are launch-bound: ~150 launches of 10-20 us per eval.  Replay the
         # eval as ONE CUDA graph from the second evaluation on (fixed buffers; the first eager run created every tensor map).
