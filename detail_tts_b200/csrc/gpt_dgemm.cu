@@ -456,7 +456,10 @@ int launch_dgemm(const dtts_dgemm_params* p, cudaStream_t st, int b_blocks) {
   rc = get_map(p->W_lo, p->w_rows, p->K, p->ldw, 128, &ml, 4);
   if (rc) return rc;
   const int nkb = p->K / 32 / p->k_splits;
-  const int stages = nkb < C::STAGES ? nkb : C::STAGES;
+  static int max_stages = -1;   // DTTS_DGEMM_STAGES: cap on the ring depth (a CTA below ~110 KB lets the next kernel's CTAs co-reside under PDL)
+  if (max_stages < 0) { const char* e = getenv("DTTS_DGEMM_STAGES"); max_stages = e ? atoi(e) : MAX_STAGES; if (max_stages < 1) max_stages = 1; }
+  int stages = nkb < C::STAGES ? nkb : C::STAGES;
+  if (stages > max_stages) stages = max_stages;
   const int slabs = ceil_div(p->N, 128);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(slabs * p->k_splits), (unsigned)b_blocks);
