@@ -8,7 +8,16 @@ import sys
 import types
 import json
 
-REF = "/root/reference"
+import os
+
+# The unmodified reference tree: /root/reference in the build container; on the GPU box the driver's snapshot carries the
+# git-ignored install baseline/_ref (copied there by __graft_entry__.build(), never committed).
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("DTTS_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/vqvae") else os.path.join(_ROOT, "baseline", "_ref"))
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, "vqvae", "model_24k.py"))
 
 
 def install():
