@@ -325,3 +325,73 @@ def test_infer_batch_continuous_runs_whole_pipeline(eos_weights, dlib):
     for b in range(10):
         assert T[b] == 0 or float(wav[b, :, :1024 * T[b]].abs().max()) > 0
         assert float(wav[b, :, 1024 * max(T[b], 0):].abs().max() if wav.shape[-1] > 1024 * max(T[b], 0) else 0.0) == 0.0
+
+
+def test_infer_batch_ragged_T_equals_per_utterance(eos_weights, dlib):
+    """the production default -- B > 1 with EOS live, so every utterance gets its own T -- through the WHOLE pipeline:
+    rows stop at different steps (injected inverse-CDF draws), an utterance whose first token is the stop token yields an empty
+    waveform instead of aborting the batch, and every other row equals its own B = 1 run (same draws, same noise)."""
+    import oracle.gpt as og
+    from detail_tts_b200.model import SynthesizerTrn
+    model = SynthesizerTrn(eos_weights, device=DEV)
+    g = torch.Generator().manual_seed(31)
+    B, G = 6, 16
+    tl = [11, 14, 9, 13, 12, 10]
+    rl = [40, 55, 48, 60, 44, 52]
+    text = torch.zeros(B, max(tl), dtype=torch.int32)
+    for b in range(B):
+        text[b, :tl[b] - 1] = torch.randint(3, 255, (tl[b] - 1,), generator=g, dtype=torch.int32)
+    refer = (torch.randn(B, 128, max(rl), generator=g) * 2 - 5).clamp(-11.5, 2.7)
+    U = torch.rand(G, B, generator=g).numpy()
+    noise0 = torch.randn(B, 128, 4 * G, generator=g)
+    steps = [torch.randn(B, 128, 4 * G, generator=g) for _ in range(50)]
+    zp = torch.randn(B, 192, 4 * G, generator=g)
+
+    def hooks(rows, u):
+        it = iter(steps)
+        return dict(multinomial=og.inverse_cdf_multinomial(u), randn=lambda s: noise0[rows, :, :s[2]],
+                    randn_like=lambda x: next(it)[rows, :, :x.shape[2]], randn_like_zp=lambda x: zp[rows, :, :x.shape[2]])
+    # which utterances produce at least one code (the noise hooks below must serve exactly those rows, in order)
+    c0 = model.gpt.inference_speech_tortoise(refer.to(DEV), rl, text, text_lengths=tl, do_sample=True, top_p=.8, temperature=.8,
+                                             repetition_penalty=2.0, max_generate_length=G, multinomial=og.inverse_cdf_multinomial(U))
+    first_stop = [int((c0[b] == 8193).float().argmax()) if bool((c0[b] == 8193).any()) else c0.shape[1] for b in range(B)]
+    kept = [b for b in range(B) if min(first_stop[b] + 1, c0.shape[1]) - 1 >= 1]
+    trb = {}
+    wav_b, wl_b = model.infer_batch(text, tl, refer, rl, max_generate_length=G, hooks=hooks(kept, U), trace=trb)
+    T = trb["T"]
+    assert [b for b in range(B) if T[b] >= 1] == kept
+    print("ragged batch: codes per utterance", T)
+    assert len(set(T)) > 2, T
+    assert wl_b.tolist() == [1024 * max(t, 0) for t in T]
+    for b in range(B):
+        if T[b] < 1:
+            assert float(wav_b[b].abs().max()) == 0
+            continue
+        tr1 = {}
+        # the B = 1 run consumes one uniform per step of ITS OWN length; rows of the batch that were already finished still
+        # consumed (ignored) draws, so the per-row sequence is simply column b
+        wav_1, wl_1 = model.infer_batch(text[b:b + 1, :tl[b]], [tl[b]], refer[b:b + 1, :, :rl[b]], [rl[b]], max_generate_length=G,
+                                        hooks=hooks([b], U[:, b:b + 1]), trace=tr1)
+        assert tr1["T"] == [T[b]] and torch.equal(tr1["codes"][0, :T[b]].cpu(), trb["codes"][kept.index(b), :T[b]].cpu()), b
+        n = int(wl_1[0])
+        e = float((wav_b[b, :, :n].double() - wav_1[0, :, :n].double()).pow(2).mean().sqrt())
+        assert e < 2e-4, (b, e)
+        assert wav_b.shape[-1] == n or float(wav_b[b, :, n:].abs().max()) == 0
+
+
+def test_second_pass_latents_equal_captured_on_ragged_batch(gpt, cfg2):
+    """UnifiedVoice.forward(return_latent=True) honours text_lengths: on a ragged batch the second-pass latents equal
+    the ones captured from the decode (the capture_latents=False path of infer_batch)."""
+    fx, text, refer = cfg2
+    B, G = 5, 10
+    tl = [51, 40, 33, 51, 45]
+    t = text[:B].clone()
+    for b in range(B):
+        t[b, tl[b] - 1:] = 0
+    gpt._states.clear()
+    codes = gpt.inference_speech_tortoise(refer[:B].to(DEV), [300] * B, t, text_lengths=tl, do_sample=False, max_generate_length=G, **COMMON)
+    cap = gpt.last_latents[:B, :G - 1].clone()
+    lat = gpt.forward(refer[:B].to(DEV), [300] * B, t, tl, codes[:, :G - 1], None, return_latent=True, clip_inputs=False)
+    e = float((cap - lat).pow(2).mean().sqrt() / lat.pow(2).mean().sqrt())
+    assert e < 1e-4, e
+    gpt._states.clear()
