@@ -47,6 +47,15 @@ constexpr int TM_S = 0;                    // S_t buffer u at columns (2t+u)*48 
 constexpr int TM_O = 2 * NT * BKV;         // O_t at columns 288 + t*48
 constexpr int TMEM_COLS = 512;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P <= 2^8 stays exact in fp16, fp32 sums have headroom
+// Every POLY_EVERY-th pair of exponentials is evaluated on the FMA pipe (Cody-Waite split + degree-4 polynomial, relative
+// error 2.7e-6 << the fp16 rounding of P) instead of MUFU.EX2: a warp-wide MUFU occupies the SFU of its SM sub-partition for
+// 8 clocks.  Measured (B200, 256 utterances x 280 frames): 238.2 us with every third pair on the polynomial, 238.3 us with none,
+// 251 us with every second -- the 5.5 extra issue slots per element cost what the shorter SFU queue saves -- so the default
+// is 0 = everything on MUFU; the path stays for parts with a lower SFU : FMA ratio.
+#ifndef DTTS_ATTN_POLY_EVERY
+#define DTTS_ATTN_POLY_EVERY 0
+#endif
+constexpr int POLY_EVERY = DTTS_ATTN_POLY_EVERY;
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -62,6 +71,26 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; a
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// 2^x for two packed values, x <= 8 (also -inf): clamp, n = round(x) by the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5],
+// 2^f by a degree-4 minimax polynomial, exponent patched with one integer multiply-add per element.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
+  float a, b;
+  up2(x2, a, b);
+  a = fmaxf(a, -126.0f); b = fmaxf(b, -126.0f);
+  const uint64_t x = pk2(a, b);
+  const uint64_t t = add2(x, pk2(12582912.0f, 12582912.0f));
+  const uint64_t n = add2(t, pk2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(n, pk2(-1.0f, -1.0f), x);
+  uint64_t q = fma2(pk2(0.009570100344717503f, 0.009570100344717503f), f, pk2(0.05591785907745361f, 0.05591785907745361f));
+  q = fma2(q, f, pk2(0.240247443318367f, 0.240247443318367f));
+  q = fma2(q, f, pk2(0.6931217908859253f, 0.6931217908859253f));
+  q = fma2(q, f, pk2(0.9999992847442627f, 0.9999992847442627f));
+  float q0, q1, t0, t1;
+  up2(q, q0, q1);
+  up2(t, t0, t1);
+  r0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  r1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 // MN-major, SWIZZLE_128B shared-memory descriptor: rows of 128 B = 64 contiguous MN elements, one row per K index,
 // 8-row swizzle atoms 1024 B apart (stride byte offset); the leading byte offset (next 64 MN elements) is unused.
@@ -138,13 +167,14 @@ struct Item { int b, h, q0, qlen, klen, nc; };
 // one item.  Every role walks the same slot stream (utterance offsets / lengths are staged in shared memory).
 struct SlotIter {
   const int* meta; int n_utt, n_heads, qblocks, stride;
-  int idx, c; Item it; bool valid;
+  uint32_t magic_pb, magic_qb;          // ceil(2^32 / (n_heads * qblocks)), ceil(2^32 / qblocks): exact quotients by __umulhi
+  int idx, c; Item it; bool valid;      // for every index below 2^32 / divisor^2 (checked on the host)
   __device__ __forceinline__ bool load(int i) {
     const int total = n_utt * n_heads * qblocks;
     for (; i < total; i += stride) {
-      it.b = i / (n_heads * qblocks);
+      it.b = (int)__umulhi((uint32_t)i, magic_pb);
       const int r = i - it.b * n_heads * qblocks;
-      it.h = r / qblocks;
+      it.h = qblocks == 1 ? r : (int)__umulhi((uint32_t)r, magic_qb);
       it.q0 = (r - it.h * qblocks) * (NT * BM);
       it.qlen = meta[MAX_UTT + it.b];
       it.klen = meta[3 * MAX_UTT + it.b];
@@ -155,6 +185,8 @@ struct SlotIter {
   }
   __device__ __forceinline__ void init(const int* m, const dtts_attention_params& p, int qb, int first, int str) {
     meta = m; n_utt = p.n_utt; n_heads = p.n_heads; qblocks = qb; stride = str;
+    magic_pb = (uint32_t)((0x100000000ull + (uint32_t)(n_heads * qb) - 1) / (uint32_t)(n_heads * qb));
+    magic_qb = (uint32_t)((0x100000000ull + (uint32_t)qb - 1) / (uint32_t)qb);
     load(first);
   }
   __device__ __forceinline__ void next() {           // advance one slot
@@ -168,10 +200,7 @@ struct SlotIter {
 __device__ __forceinline__ void mbar_wait_lite(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++n > (1u << 26)) {
-      printf("dtts attn_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (++n > (1u << 26)) __trap();      // no printf: its argument set-up bloated every wait site (the loop is icache-sensitive)
   }
 }
 
@@ -362,6 +391,15 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld32_nowait(ts_addr, s);
         tmem_ld16(ts_addr + 32, s + 32);
         tmem_wait_ld();
+        if (k0 + BKV > it.klen) {
+          // keys beyond the utterance (separator / next utterance's rows) -> -inf.  Done on the raw scores IN PLACE (the
+          // scale is positive: -inf survives the FMA below) with predicated moves: a select in a branch made the compiler
+          // permute all 48 score registers around the join on every slot.
+          const int nv = it.klen - k0;      // 1 .. BKV-1 valid keys in this chunk (warp-uniform)
+#pragma unroll
+          for (int j = 1; j < BKV; ++j)
+            asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %1, %2;\n\t@p mov.b32 %0, 0xFF800000;\n\t}" : "+f"(s[j]) : "r"(nv), "r"(j));
+        }
         // scores in the log2 domain: s*scale*log2e + bias*log2e, two columns per FFMA2
         uint64_t sp[BKV / 2];
         const uint64_t sc22 = pk2(sc2, sc2);
@@ -385,11 +423,6 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
 #pragma unroll
         for (int j = 0; j < BKV; j += 2) up2(sp[j / 2], s[j], s[j + 1]);
-        if (k0 + BKV > it.klen) {
-#pragma unroll
-          for (int j = 0; j < BKV; ++j)
-            if (k0 + j >= it.klen) s[j] = -INFINITY;
-        }
         float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
         for (int j = 4; j < BKV; j += 4) {
@@ -408,10 +441,22 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint64_t la = pk2(0.f, 0.f), lb = pk2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < BKV; j += 4) {
-          float a0, a1, b0, b1;
-          up2(add2(pk2(s[j], s[j + 1]), nm2), a0, a1);
-          up2(add2(pk2(s[j + 2], s[j + 3]), nm2), b0, b1);
-          const float p0 = ex2f(a0), p1 = ex2f(a1), p2 = ex2f(b0), p3 = ex2f(b1);
+          const uint64_t xa = add2(sp[j / 2], nm2), xb = add2(sp[j / 2 + 1], nm2);
+          float p0, p1, p2, p3;
+          if (POLY_EVERY > 0 && (j / 2) % (POLY_EVERY > 0 ? POLY_EVERY : 1) == POLY_EVERY - 1) {
+            exp2_poly2(xa, p0, p1);
+          } else {
+            float a0, a1;
+            up2(xa, a0, a1);
+            p0 = ex2f(a0); p1 = ex2f(a1);
+          }
+          if (POLY_EVERY > 0 && (j / 2 + 1) % (POLY_EVERY > 0 ? POLY_EVERY : 1) == POLY_EVERY - 1) {
+            exp2_poly2(xb, p2, p3);
+          } else {
+            float b0, b1;
+            up2(xb, b0, b1);
+            p2 = ex2f(b0); p3 = ex2f(b1);
+          }
           la = add2(la, pk2(p0, p1));
           lb = add2(lb, pk2(p2, p3));
           pk[j / 2] = pack_h2(p0, p1);
@@ -451,7 +496,7 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (sl.last_chunk()) {                                  // remember what the deferred epilogue needs
         prev_live = warp_live;
         prev_store = warp_live && qi < it.qlen;
-        prev_inv = 1.0f / l_run;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(prev_inv) : "f"(l_run));   // 1 ulp; the IEEE division's slow path was a CALL in the loop
         prev_row = (long)(p.o_off ? p.o_off[it.b] : meta[it.b]) + qi;
         prev_h = it.h;
       }
@@ -483,6 +528,7 @@ extern "C" int dtts_attention_f16_tc(const dtts_attention_params* p, void* strea
   DTTS_REQUIRE(p && p->q && p->k && p->v && p->q_off && p->q_len && p->k_off && p->k_len, "attention_f16_tc: null argument");
   DTTS_REQUIRE(p->is_f16 && p->head_dim == HD, "attention_f16_tc: needs fp16 operands and head_dim 48");
   DTTS_REQUIRE(!p->causal, "attention_f16_tc: causal masks are not supported (use dtts_attention_f32)");
+  DTTS_REQUIRE(p->scale > 0.f, "attention_f16_tc: the score scale must be positive");
   DTTS_REQUIRE(p->bias_mode == DTTS_ATTN_BIAS_NONE || (p->bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE && p->bias_table),
                "attention_f16_tc: unsupported bias mode");
   const int bias_floats = p->bias_mode == DTTS_ATTN_BIAS_RELPOS_TABLE ? p->n_heads * (2 * p->bias_half + 1 + 2 * BIAS_PAD) : 0;
@@ -518,6 +564,7 @@ extern "C" int dtts_attention_f16_tc(const dtts_attention_params* p, void* strea
   if (rc) return rc;
   const int qblocks = ceil_div(p->max_q_len, NT * BM);
   const long items = (long)p->n_utt * p->n_heads * qblocks;
+  DTTS_REQUIRE(items * p->n_heads * qblocks < (1l << 31), "attention_f16_tc: too many work items for the reciprocal-multiply item split");
   const int grid = items < g_sms ? (int)items : g_sms;
   {
     cudaError_t le = launch_maybe_pdl(flash48_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem_bytes, (cudaStream_t)stream, mq, mk, mv, *p, qblocks);

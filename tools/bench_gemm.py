@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from detail_tts_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
+L = _lib.Lib(os.environ["DTTS_LIB"]) if os.environ.get("DTTS_LIB") else _lib.lib()   # DTTS_LIB: an A/B build of the library
 dev = "cuda"
 M = int(os.environ.get("M", 71936))
 SHAPES = [  # name, N, K, taps, res, out32, out16
