@@ -37,16 +37,24 @@ constexpr int epi_stage_bytes(int bn, bool tf32) { return EPI_WARPS * 32 * ((bn 
 // CTAS = 2: cta_group::2 -- a pair of CTAs (one cluster, two SMs of a TPC) computes a 256 x BN tile; each CTA stages its own
 // 128 rows of A and HALF of the B tile, the leader's tcgen05.mma reads both halves, each CTA's TMEM receives its 128 rows
 // of the accumulator.  Shared-memory operand traffic per SM per MMA drops from 4 + BN/32 KB to 4 + BN/64 KB.
-template <int BN, bool TF32 = false, int CTAS = 1>
+// EPI: 0 = register/LSU epilogue (every activation / row map / accumulate variant), 1 = fp16-only output through per-warp
+// TMA stores, 2 = fp32 output (+ fp32 residual) through per-warp TMA loads and stores (see the epilogue below).
+constexpr int EPI_BUF_BYTES = 4096;      // one per-warp TMA box: 32 rows x 128 bytes (32 fp32 or 64 fp16 columns), 128B swizzle
+constexpr int epi_bufs(int epi) { return epi == 2 ? 3 : 1; }
+constexpr int BAR_BYTES = 512;
+template <int BN, bool TF32 = false, int CTAS = 1, int EPI = 0>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // rows of B staged by one CTA x 128 B, for fp16 (64 el) and tf32 (32 el) alike
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
-  static constexpr int EPI_STAGE_BYTES = epi_stage_bytes(BN, TF32);
-  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;
+  static constexpr int EPI_STAGE_BYTES = EPI == 0 ? epi_stage_bytes(BN, TF32) : EPI_WARPS * epi_bufs(EPI) * EPI_BUF_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = 2 * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+  // layout: [operand stages | epilogue staging (1024-byte aligned: the stages are multiples of 1 KB) | barriers]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_STAGE_BYTES;
+  static_assert(STAGE_BYTES % 1024 == 0, "swizzled tiles and TMA boxes need 1024-byte aligned bases");
+  static_assert(STAGES >= 2, "operand ring too shallow");
 };
 
 // GroupNorm statistics of the output tile, accumulated by the epilogue (EpiParams.gn_stats): this lane's per-row partial
@@ -90,13 +98,15 @@ __device__ __forceinline__ void gn_accumulate(float* stats, int groups, int g, c
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int BN, bool TF32, int CTAS = 1, bool GN = false>
+template <int BN, bool TF32, int CTAS = 1, bool GN = false, int EPI = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride,
                const int kb_per_split, const long split_stride, const int debug) {
-  using C = Cfg<BN, TF32, CTAS>;
+  using C = Cfg<BN, TF32, CTAS, EPI>;
+  static_assert(EPI == 0 || !TF32, "the TMA epilogues are fp16-GEMM only");
   static_assert(CTAS == 1 || !TF32, "the CTA-pair variant is fp16 only");
   uint32_t cta_rank = 0;
   if (CTAS == 2) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -107,13 +117,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries of the SHARED address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* epi_region = smem + C::STAGES * C::STAGE_BYTES;      // 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(epi_region + C::EPI_STAGE_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + C::STAGES;          // [STAGES]
   uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
   uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * C::STAGES + 4);
-  float* epi_stage = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256);
+  uint64_t* ebars = bars + 2 * C::STAGES + 6;  // [EPI_WARPS][3]: residual boxes landed (EPI == 2)
+  static_assert((2 * 8 + 6 + EPI_WARPS * 3) * 8 <= BAR_BYTES, "barrier block too small");
+  float* epi_stage = (float*)epi_region;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CTAS * EPI_WARPS); }
+    if (EPI == 2) for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(&ebars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -161,6 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (TF32) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
+      }
+      if (EPI != 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO) : "memory");
+        if (EPI == 2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
       }
       int stage = 0; uint32_t phase = 0;
       for (int tile = work_id; tile < num_tiles; tile += work_stride) {
@@ -239,6 +257,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ epilogue warps ===============================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int cpar = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks c = cpar, cpar+2, ...
+    if constexpr (EPI != 0) {
+      // ---------------------------------------------------------------- TMA epilogues (round 3)
+      // The register/LSU epilogue below moves a 128 x 256 fp32 tile (+ its residual) at ~19 GB/s per SM: ncu shows the epilogue
+      // warps parked on the first instruction that reuses an address register of their LDG.128s (the LSU queue is backed up),
+      // whatever the number of loads in flight (two-deep register prefetch and an L2 prefetch of the residual tile both
+      // measured neutral).  Here every epilogue warp owns 32 accumulator rows (its TMEM lane quarter) x 128-byte chunks and
+      // talks to HBM only through the TMA unit: one thread per row, the row's 128 bytes live in a 128B-swizzled per-warp box
+      // (chunk k of row r at k ^ (r & 7): conflict-free for row-per-lane AND for the transposed statistics pass), so there is
+      // no transpose, no per-lane address arithmetic and no LSU global access at all.
+      //   EPI == 2: fp32 output (+ fp32 residual).  Three boxes per warp: the residual boxes of the next two chunks are in
+      //             flight (across tile boundaries, i.e. during the next tile's main loop) while the current one is updated
+      //             in place and stored.
+      //   EPI == 1: fp16-only output, 64 columns per box, one box per warp.
+      // Separator rows (row_utt < 0) are written as zeros: they are zero in every rows-layout buffer.
+      constexpr int NB = EPI == 2 ? 3 : 1;
+      constexpr int CW = EPI == 2 ? 32 : 64;     // columns per chunk = one 128-byte box row
+      constexpr int NCH = BN / CW;               // chunks per tile; this warp takes c = cpar, cpar + 2, ...
+      const int ew = warp - 2;
+      uint8_t* ebuf = epi_region + ew * NB * EPI_BUF_BYTES;
+      uint64_t* ebar = ebars + ew * 3;
+      const int r7 = lane & 7;
+      const bool gn = GN && epi.gn_stats != nullptr;
+      const int gn_groups = gn ? epi.N / epi.gn_cpg : 0;
+      const bool has_res = EPI == 2 && epi.res != nullptr;
+      const float alpha = epi.alpha;
+      // load cursor: walks the same (tile, chunk) sequence as the compute loop, NB - 1 chunks ahead
+      int ld_tile = work_id, ld_c = cpar;
+      uint32_t ld_seq = 0, use_seq = 0;
+      auto ld_normalize = [&]() {
+        while (ld_tile < num_tiles && (ld_c >= NCH || (ld_tile % n_tiles) * BN + ld_c * CW >= epi.N)) { ld_tile += work_stride; ld_c = cpar; if (cpar >= NCH) { ld_tile = num_tiles; } }
+      };
+      auto issue_load = [&]() {
+        if (ld_tile >= num_tiles) return;
+        if (lane == 0) {
+          const int b = (int)(ld_seq % NB);
+          mbar_expect_tx(&ebar[b], EPI_BUF_BYTES);
+          tma_load_2d(ebuf + b * EPI_BUF_BYTES, &tmR, &ebar[b], (ld_tile % n_tiles) * BN + ld_c * CW,
+                      (ld_tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM + q * 32);
+        }
+        ++ld_seq;
+        ld_c += 2;
+        ld_normalize();
+      };
+      ld_normalize();
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < NB - 1; ++i) issue_load();
+      }
+      int acc = 0; uint32_t acc_phase = 0;
+      // utterance id of this lane's row, fetched one tile ahead (its L2 latency was 7 % of the epilogue warps' time)
+      auto own_utt = [&](int t) -> int {
+        if (t >= num_tiles) return -1;
+        const int m = (t / n_tiles) * (CTAS * BM) + (int)cta_rank * BM + q * 32 + lane;
+        return m < epi.M ? (epi.row_utt ? __ldg(epi.row_utt + m) : 0) : -1;
+      };
+      int utt_next = own_utt(work_id);
+      // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has landed, and the
+      // arrive comes from lane 1: lane 0 has TMA stores in flight, and the cluster-scope release of the CTA-pair arrive
+      // (MEMBAR + ERRBAR) made it wait for them -- 25 % of the epilogue warps' samples, with the tensor pipe idle behind it.
+      auto release_acc = [&](int a) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 1) {
+          if (CTAS == 2) mbar_arrive_leader(&tempty[a]);
+          else mbar_arrive(&tempty[a]);
+        }
+      };
+      for (int tile = work_id; tile < num_tiles; tile += work_stride) {
+        const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
+        const int n0 = (tile % n_tiles) * BN;
+        const bool valid = utt_next >= 0;
+        utt_next = own_utt(tile + work_stride);
+        int uid[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) uid[it] = 0;
+        if (GN && epi.row_utt) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = m0 + q * 32 + (lane >> 3) + it * 4;
+            uid[it] = m < epi.M ? __ldg(epi.row_utt + m) : -1;
+          }
+        }
+        int c_last = -1;                             // this warp's last chunk of the tile
+        for (int c = cpar; c < NCH && n0 + c * CW < epi.N && debug != 1; c += 2) c_last = c;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        if (c_last < 0) release_acc(acc);
+#pragma unroll 1
+        for (int c = cpar; c <= c_last; c += 2) {
+          const int nc = n0 + c * CW;
+          const int b = (int)(use_seq % NB);
+          uint8_t* box = ebuf + b * EPI_BUF_BYTES;
+          uint8_t* row = box + lane * 128;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * CW);
+          if constexpr (EPI == 2) {
+            float4 bb[8];                              // bias of the chunk's 32 columns: requested before the TMEM load
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              bb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (epi.bias && nc + 4 * k < epi.N) bb[k] = __ldg(reinterpret_cast<const float4*>(epi.bias + nc) + k);
+            }
+            float v[32];
+            tmem_ld32(taddr, v);
+            if (c == c_last) release_acc(acc);
+            if (has_res) {
+              mbar_wait(&ebar[b], (use_seq / NB) & 1u);
+            } else {
+              if (lane == 0) bulk_wait_read<NB - 1>();       // the store that last used this box has read it
+              __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float4* p4 = reinterpret_cast<float4*>(row + ((k ^ r7) << 4));
+              float4 w = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              w.x += bb[k].x; w.y += bb[k].y; w.z += bb[k].z; w.w += bb[k].w;
+              if (has_res) { const float4 r = *p4; w.x += r.x; w.y += r.y; w.z += r.z; w.w += r.w; }
+              if (alpha != 1.0f) { w.x *= alpha; w.y *= alpha; w.z *= alpha; w.w *= alpha; }
+              if (!valid) w = make_float4(0.f, 0.f, 0.f, 0.f);
+              *p4 = w;
+            }
+          } else {
+            float4 bb[16];                             // bias of the chunk's 64 columns: requested before the TMEM loads
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              bb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (epi.bias && nc + 4 * k < epi.N) bb[k] = __ldg(reinterpret_cast<const float4*>(epi.bias + nc) + k);
+            }
+            float v[32], v2[32];
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + 32, v2);
+            if (c == c_last) release_acc(acc);
+            uint4 pk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {        // 16-byte chunk k = columns 8k .. 8k+7
+              float w[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] = k < 4 ? v[8 * k + e] : v2[8 * (k - 4) + e];
+              {
+                const float4 b0 = bb[2 * k], b1 = bb[2 * k + 1];
+                w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w; w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (alpha != 1.0f) w[e] *= alpha;
+                if (!valid) w[e] = 0.f;
+              }
+              __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
+              __half2 h2 = __floats2half2_rn(w[4], w[5]), h3 = __floats2half2_rn(w[6], w[7]);
+              pk[k].x = *reinterpret_cast<uint32_t*>(&h0); pk[k].y = *reinterpret_cast<uint32_t*>(&h1);
+              pk[k].z = *reinterpret_cast<uint32_t*>(&h2); pk[k].w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            if (lane == 0) bulk_wait_read<0>();            // the previous store has read the (single) box
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ r7) << 4)) = pk[k];
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && debug != 2) {            // DTTS_GEMM_DEBUG=2: everything but the stores (timing experiments)
+            tma_store_2d(&tmO, box, nc, m0 + q * 32);
+            bulk_commit();
+          }
+          if (GN && gn) {
+            // statistics of the stored values (fp32 / the fp16-rounded outputs): transposed read of the box, lane = rows
+            // (lane >> 3) + 4 it, 16-byte chunk lane & 7 (4 fp32 / 8 fp16 columns, all inside one group: gn_cpg % 8 == 0)
+            float ps[8], pss[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = (lane >> 3) + it * 4;
+              const uint4 t = *reinterpret_cast<const uint4*>(box + rr * 128 + ((r7 ^ (rr & 7)) << 4));
+              if constexpr (EPI == 2) {
+                const float a0 = __uint_as_float(t.x), a1 = __uint_as_float(t.y), a2 = __uint_as_float(t.z), a3 = __uint_as_float(t.w);
+                ps[it] = (a0 + a1) + (a2 + a3);
+                pss[it] = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3)));
+              } else {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t.w));
+                ps[it] = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+                pss[it] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, f3.y * f3.y)))))));
+              }
+            }
+            gn_accumulate(epi.gn_stats, gn_groups, (nc + r7 * (EPI == 2 ? 4 : 8)) / epi.gn_cpg, uid, ps, pss, lane);
+          }
+          ++use_seq;
+          if (has_res) {
+            // refill the box of the PREVIOUS chunk (its store is the older of the two pending groups) with the residual of the
+            // chunk after the next; every lane's reads of that box (statistics pass) precede the async write
+            if (lane == 0) bulk_wait_read<1>();
+            fence_proxy_async();
+            __syncwarp();
+            issue_load();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) bulk_wait_all();          // shared memory must outlive the last stores
+    } else {
     constexpr bool WIDE_OK = BN >= 256 && !TF32;
     float* st = epi_stage + (warp - 2) * 32 * (WIDE_OK ? EPI_LD_W : EPI_LD);
     const int cc = (lane & 7) * 4;
@@ -427,6 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }   // EPI == 0
   }
 
   tc_fence_before();
@@ -479,12 +695,26 @@ int g_sm_count = 0;
 int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
 // CTA-pair (cta_group::2) launch: fp16 only, 256 x BN tiles, one 2-CTA cluster per tile stream
-template <int BN, bool GN = false>
+// tensor maps of the TMA epilogues: per-warp boxes of 32 rows x 128 bytes over the output (EPI 1: fp16, EPI 2: fp32) and the
+// fp32 residual.  Unused maps alias the A map (never dereferenced).
+template <int EPI>
+int epi_maps(const dtts_gemm_params* p, const CUtensorMap& dflt, CUtensorMap* mo, CUtensorMap* mr) {
+  *mo = dflt; *mr = dflt;
+  if (EPI == 1) return get_map(p->out_f16, p->M, p->N, p->ldo16, 32, mo, 2);
+  if (EPI == 2) {
+    int rc = get_map(p->out_f32, p->M, p->N, p->ldo32, 32, mo, 4);
+    if (rc) return rc;
+    if (p->res) return get_map(p->res, p->M, p->N, p->ldr, 32, mr, 4);
+  }
+  return 0;
+}
+
+template <int BN, bool GN = false, int EPI = 0>
 int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
-  using C = Cfg<BN, false, 2>;
+  using C = Cfg<BN, false, 2, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, 2, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, 2, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc pair<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -492,6 +722,9 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma, 2);
   if (rc) return rc;
   rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN / 2, &mw, 2);
+  if (rc) return rc;
+  CUtensorMap mo, mr;
+  rc = epi_maps<EPI>(p, ma, &mo, &mr);
   if (rc) return rc;
   const int pairs = ceil_div(p->M, 2 * BM) * ceil_div(p->N, BN);
   const int kb_all = ceil_div(p->K, 64);
@@ -509,19 +742,19 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_dtts_pdl ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2, GN>, ma, mw, ma, mw, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2, GN, EPI>, ma, mw, ma, mw, mo, mr, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
                                       kb_all, (long)0, g_debug);
   if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc pair launch failed: %s", cudaGetErrorString(le));
   DTTS_CHECK_LAUNCH("gemm_tc_pair");
   return 0;
 }
 
-template <int BN, bool TF32, bool GN = false>
+template <int BN, bool TF32, bool GN = false, int EPI = 0>
 int launch(const dtts_gemm_params* p, cudaStream_t st) {
-  using C = Cfg<BN, TF32>;
+  using C = Cfg<BN, TF32, 1, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, 1, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, 1, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) DTTS_FAIL(-3, "cudaFuncSetAttribute(gemm_tc<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -538,6 +771,9 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
     rc = get_map(p->W_lo, p->taps * p->N, p->K, p->ldw, BN, &mw2, es);
     if (rc) return rc;
   }
+  CUtensorMap mo, mr;
+  rc = epi_maps<EPI>(p, ma, &mo, &mr);
+  if (rc) return rc;
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, BN);
   const int kb_all = ceil_div(p->K, TF32 ? 32 : 64);
   int splits = TF32 && p->split_k > 1 ? p->split_k : 1;
@@ -551,8 +787,8 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
   }
   dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
   {
-    cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32, 1, GN>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, e, p->K, p->taps,
-                                      p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
+    cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32, 1, GN, EPI>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, mo, mr, e,
+                                      p->K, p->taps, p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
     if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc launch failed: %s", cudaGetErrorString(le));
   }
   DTTS_CHECK_LAUNCH("gemm_tc");
@@ -636,19 +872,52 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   // bench shape (M = 72k rows) the 256-wide shapes win; on a 1/8 shard (M = 9k) 256-wide tiles leave the second wave
   // 42 % full and the 192-wide shape is ~20 % cheaper.
   const bool gs = p->gn_stats != nullptr;
-  const bool can_pair = pair && N % 256 == 0 && p->M >= 4096 && (long)p->K * p->taps >= 1536;
-  const bool can256 = bn256 && N % 256 == 0, can192 = N % 192 == 0;
+  // TMA epilogues (EPI 1 / 2, see the kernel): the plain bias / residual / alpha epilogue of the diffusion convs with 16-byte
+  // aligned rows; everything else (activations, row maps, accumulate, per-utterance bias, both outputs) stays on EPI 0.
+  static int tma_epi = -1;
+  if (tma_epi < 0) { const char* e = getenv("DTTS_GEMM_TMAEPI"); tma_epi = e ? atoi(e) : 3; }
+  int epi = 0;
+  if (tma_epi && p->act == DTTS_ACT_NONE && !p->bias_utt && !p->out_row_map && !p->accumulate && (N & 3) == 0 &&
+      (!p->bias || (((uintptr_t)p->bias) & 15) == 0) && (g_debug == 0 || g_debug == 1 || g_debug == 2)) {
+    if (p->out_f16 && !p->out_f32 && !p->res && p->act16 == DTTS_ACT_NONE && (p->ldo16 & 7) == 0 && (((uintptr_t)p->out_f16) & 15) == 0 &&
+        (!gs || (N & 63) == 0))
+      epi = 1;
+    else if (p->out_f32 && !p->out_f16 && (p->ldo32 & 3) == 0 && (((uintptr_t)p->out_f32) & 15) == 0 &&
+             (!p->res || ((p->ldr & 3) == 0 && (((uintptr_t)p->res) & 15) == 0)) && (!gs || (N & 31) == 0))
+      epi = 2;
+    if (epi & tma_epi) {} else epi = 0;          // DTTS_GEMM_TMAEPI = 0 / 1 / 2 / 3: off / fp16 stores only / fp32 only / both (default)
+  }
+  // the fp32 + residual boxes need 96 KB: a single-CTA 256-wide tile would be left with two operand stages, so those GEMMs
+  // take the CTA-pair tile (32 KB stages) whatever their K
+  static int pair_mink = -1;   // smallest K * taps that takes the CTA-pair tile
+  if (pair_mink < 0) { const char* e = getenv("DTTS_GEMM_PAIR_MINK"); pair_mink = e ? atoi(e) : 768; }
+  const bool can_pair = pair && N % 256 == 0 && p->M >= 4096 && ((long)p->K * p->taps >= pair_mink || epi == 2);
+  const bool can256 = bn256 && N % 256 == 0 && epi != 2, can192 = N % 192 == 0;
+#define DTTS_LAUNCH(BN_, PAIR_)                                                                                      \
+  do {                                                                                                               \
+    if (PAIR_) {                                                                                                     \
+      if (epi == 2) return gs ? launch_pair<BN_, true, 2>(p, st) : launch_pair<BN_, false, 2>(p, st);                \
+      if (epi == 1) return gs ? launch_pair<BN_, true, 1>(p, st) : launch_pair<BN_, false, 1>(p, st);                \
+      return gs ? launch_pair<BN_, true>(p, st) : launch_pair<BN_>(p, st);                                           \
+    }                                                                                                                \
+    if (epi == 2) return gs ? launch<BN_, false, true, 2>(p, st) : launch<BN_, false, false, 2>(p, st);              \
+    if (epi == 1) return gs ? launch<BN_, false, true, 1>(p, st) : launch<BN_, false, false, 1>(p, st);              \
+    return gs ? launch<BN_, false, true>(p, st) : launch<BN_, false>(p, st);                                         \
+  } while (0)
   if ((can_pair || can256) && can192) {
     const long mt = ceil_div(p->M, BM), mt2 = ceil_div(p->M, 2 * BM);
     const double c256 = (double)((mt * (N / 256) + g_sm_count - 1) / g_sm_count) * 256.0;
     const double c192 = (double)((mt * (N / 192) + g_sm_count - 1) / g_sm_count) * 192.0 / 0.95;
     const double cpair = (double)((mt2 * (N / 256) + g_sm_count / 2 - 1) / (g_sm_count / 2)) * 256.0 / 1.08;
-    if (c192 < (can256 ? c256 : 1e30) && c192 < (can_pair ? cpair : 1e30)) return gs ? launch<192, false, true>(p, st) : launch<192, false>(p, st);
-    if (can_pair && (!can256 || cpair <= c256)) return gs ? launch_pair<256, true>(p, st) : launch_pair<256>(p, st);
+    if (c192 < (can256 ? c256 : 1e30) && c192 < (can_pair ? cpair : 1e30)) DTTS_LAUNCH(192, false);
+    if (can_pair && (!can256 || cpair <= c256)) DTTS_LAUNCH(256, true);
   }
-  if (can_pair) return gs ? launch_pair<256, true>(p, st) : launch_pair<256>(p, st);
-  if (can256) return gs ? launch<256, false, true>(p, st) : launch<256, false>(p, st);
-  if (can192) return gs ? launch<192, false, true>(p, st) : launch<192, false>(p, st);
+  if (can_pair) DTTS_LAUNCH(256, true);
+  if (can256) DTTS_LAUNCH(256, false);
+  if (can192) DTTS_LAUNCH(192, false);
+#undef DTTS_LAUNCH
+  epi = 0;
+  if (bn256 && N % 256 == 0) return gs ? launch<256, false, true>(p, st) : launch<256, false>(p, st);   // EPI 2 without a CTA pair: legacy epilogue
   DTTS_REQUIRE(!gs, "gemm_f16_tc: gn_stats is implemented for N %% 192 == 0 or N %% 256 == 0");
   if (N > 64) return launch<128, false>(p, st);
   if (N > 32) return launch<64, false>(p, st);

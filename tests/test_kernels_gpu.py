@@ -148,6 +148,51 @@ def test_gemm_tc_back_to_back_determinism(dlib):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("M,N,K,taps,mode", [
+    (40000, 768, 768, 1, "res32"),      # 1x1 + residual in place: CTA-pair tiles, several tiles per CTA (loads run across tiles)
+    (40000, 768, 768, 3, "res32"),      # k3 + residual
+    (9000, 768, 768, 1, "res32"),       # small shard: 192-wide single-CTA tiles with the three-box pipeline
+    (40000, 2304, 768, 1, "f16"),       # fp16-only output through TMA stores (256-wide, four operand stages)
+    (9000, 768, 768, 1, "f16"),         # ... 192-wide: three 64-column boxes shared unevenly by the two warps of a quarter
+    (5000, 256, 768, 3, "out32"),       # fp32 output without residual (store-only box reuse)
+    (37, 768, 768, 1, "res32"),         # less than one tile
+])
+def test_gemm_tma_epilogue(dlib, M, N, K, taps, mode):
+    """The TMA epilogues (per-warp swizzled boxes, residual boxes loaded two chunks ahead, TMA stores): result == reference
+    for ragged utterances (separator rows are written as zeros), alpha != 1, residual == output buffer (in place)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + taps)
+    A = torch.randn(M, K, generator=g, device=DEV).half()
+    W = (torch.randn(taps * N, K, generator=g, device=DEV) / math.sqrt(K * taps)).half()
+    bias = torch.randn(N, generator=g, device=DEV)
+    ru = torch.zeros(M, dtype=torch.int32, device=DEV)
+    sep = torch.randperm(M, generator=g, device=DEV)[:max(1, M // 50)]
+    ru[sep] = -1
+    ru[M // 2:M // 2 + 40] = -1          # a whole 32-row strip of separator rows
+    if mode == "res32":
+        x = torch.randn(M, N, generator=g, device=DEV)
+        x[ru < 0] = 0
+        ref = gemm_ref(A, W, N, taps, -(taps // 2), 1, bias=bias, row_utt=ru, res=x, alpha=0.75)
+        dlib.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2), tap_stride=1,
+                  bias=bias, row_utt=ru, res=x, ldr=N, out_f32=x, ldo32=N, act=0, alpha=0.75)
+        out, tol = x, 3e-4
+    elif mode == "out32":
+        out = torch.full((M, N), 3.0, device=DEV)
+        ref = gemm_ref(A, W, N, taps, -(taps // 2), 1, bias=bias, row_utt=ru, alpha=1.0)
+        dlib.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2), tap_stride=1,
+                  bias=bias, row_utt=ru, out_f32=out, ldo32=N, act=0, alpha=1.0)
+        tol = 3e-4
+    else:
+        out = torch.full((M, N), 3.0, device=DEV, dtype=torch.float16)
+        ref = gemm_ref(A, W, N, taps, -(taps // 2), 1, bias=bias, row_utt=ru, alpha=1.0)
+        dlib.call("dtts_gemm_f16_tc", A=A, W=W, M=M, N=N, K=K, lda=K, ldw=K, taps=taps, tap_shift0=-(taps // 2), tap_stride=1,
+                  bias=bias, row_utt=ru, out_f16=out, ldo16=N, act=0, alpha=1.0)
+        tol = 3e-3
+    torch.cuda.synchronize()
+    assert out[ru < 0].abs().max().item() == 0          # separator rows: zeros
+    err = (out.double() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+
+
 def _layout(lens, gap, dev=DEV):
     off, o = [], gap
     for n in lens:
