@@ -40,13 +40,15 @@ constexpr int epi_stage_bytes(int bn, bool tf32) { return EPI_WARPS * 32 * ((bn 
 // EPI: 0 = register/LSU epilogue (every activation / row map / accumulate variant), 1 = fp16-only output through per-warp
 // TMA stores, 2 = fp32 output (+ fp32 residual) through per-warp TMA loads and stores (see the epilogue below).
 constexpr int EPI_BUF_BYTES = 4096;      // one per-warp TMA box: 32 rows x 128 bytes (32 fp32 or 64 fp16 columns), 128B swizzle
-constexpr int epi_bufs(int epi) { return epi == 2 ? 3 : 1; }
+// boxes per epilogue warp: EPI 2 keeps two residual boxes in flight; EPI 1 double-buffers its stores where the 32 KB stages of
+// the CTA-pair tiles leave room (a single-CTA 256-wide tile would drop to three operand stages)
+constexpr int epi_bufs(int epi, int ctas) { return epi == 2 ? 3 : (ctas == 2 ? 2 : 1); }
 constexpr int BAR_BYTES = 512;
 template <int BN, bool TF32 = false, int CTAS = 1, int EPI = 0>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // rows of B staged by one CTA x 128 B, for fp16 (64 el) and tf32 (32 el) alike
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
-  static constexpr int EPI_STAGE_BYTES = EPI == 0 ? epi_stage_bytes(BN, TF32) : EPI_WARPS * epi_bufs(EPI) * EPI_BUF_BYTES;
+  static constexpr int EPI_STAGE_BYTES = EPI == 0 ? epi_stage_bytes(BN, TF32) : EPI_WARPS * epi_bufs(EPI, CTAS) * EPI_BUF_BYTES;
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = 2 * BN;
@@ -104,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                EpiParams epi, const int K, const int taps, const int tap_shift0, const int tap_stride,
-               const int kb_per_split, const long split_stride, const int debug) {
+               const int kb_per_split, const long split_stride, const int debug, const int slab_bytes, const int n_slab, const int n_wst) {
   using C = Cfg<BN, TF32, CTAS, EPI>;
   static_assert(EPI == 0 || !TF32, "the TMA epilogues are fp16-GEMM only");
   static_assert(CTAS == 1 || !TF32, "the CTA-pair variant is fp16 only");
@@ -119,13 +121,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_region = smem + C::STAGES * C::STAGE_BYTES;      // 1024-byte aligned
   uint64_t* bars = (uint64_t*)(epi_region + C::EPI_STAGE_BYTES);
-  uint64_t* full = bars;                       // [STAGES]
-  uint64_t* empty = bars + C::STAGES;          // [STAGES]
-  uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
-  uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * C::STAGES + 4);
-  uint64_t* ebars = bars + 2 * C::STAGES + 6;  // [EPI_WARPS][3]: residual boxes landed (EPI == 2)
-  static_assert((2 * 8 + 6 + EPI_WARPS * 3) * 8 <= BAR_BYTES, "barrier block too small");
+  uint64_t* full = bars;                       // [8]
+  uint64_t* empty = bars + 8;                  // [8]
+  uint64_t* tfull = bars + 16;                 // [2]
+  uint64_t* tempty = bars + 18;                // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+  uint64_t* ebars = bars + 22;                 // [EPI_WARPS][3]: residual boxes landed (EPI == 2)
+  // Slab mode (multi-tap convs, slab_bytes > 0; see the producer): the operand space is re-cut into a ring of n_slab A slabs and
+  // a ring of n_wst weight tiles; full / empty above serve the weight ring (n_wst <= 8), these the slab ring (n_slab <= 4).
+  uint64_t* sfull = ebars + EPI_WARPS * 3;     // [4]
+  uint64_t* sempty = sfull + 4;                // [4]
+  static_assert((2 * 8 + 6 + EPI_WARPS * 3 + 8) * 8 <= BAR_BYTES, "barrier block too small");
+  const bool slab = !TF32 && slab_bytes > 0;
+  uint8_t* wring = smem + n_slab * slab_bytes; // weight ring behind the slabs (slab mode)
   float* epi_stage = (float*)epi_region;
 
   const int warp = threadIdx.x >> 5;
@@ -142,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (epi.out_f32) epi.out_f32 += (long)blockIdx.y * split_stride;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CTAS * EPI_WARPS); }
     if (EPI == 2) for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(&ebars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,6 +190,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EPI == 2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
       }
       int stage = 0; uint32_t phase = 0;
+      if (slab) {
+        // Multi-tap convs: per K block ONE slab of A rows [m0 + shift0, m0 + shift0 + 128 + (taps-1)*stride) (a single TMA box) serves
+        // every tap -- tap t is the same slab read from row t*stride on (a shifted UMMA descriptor) -- instead of one shifted
+        // 128-row tile per tap: the A traffic of a k3 conv drops 3x, of the vocoder's k11 convs 11x.  Weight tiles stream
+        // through their own ring, tap by tap.
+        int ss = 0; uint32_t sphase = 0;
+        for (int tile = work_id; tile < num_tiles; tile += work_stride) {
+          const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
+          const int n0 = (tile % n_tiles) * BN + (int)cta_rank * (BN / CTAS);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&sempty[ss], sphase ^ 1);
+            if (CTAS == 2) {
+              if (leader) mbar_expect_tx(&sfull[ss], 2 * slab_bytes);
+              tma_load_2d_pair(smem + ss * slab_bytes, &tmA, &sfull[ss], (kb0 + kb) * BKE, m0 + tap_shift0);
+            } else {
+              mbar_expect_tx(&sfull[ss], slab_bytes);
+              tma_load_2d(smem + ss * slab_bytes, &tmA, &sfull[ss], (kb0 + kb) * BKE, m0 + tap_shift0);
+            }
+            if (++ss == n_slab) { ss = 0; sphase ^= 1; }
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (CTAS == 2) {
+                if (leader) mbar_expect_tx(&full[stage], 2 * C::B_BYTES);
+                tma_load_2d_pair(wring + stage * C::B_BYTES, &tmW, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
+              } else {
+                mbar_expect_tx(&full[stage], C::B_BYTES);
+                tma_load_2d(wring + stage * C::B_BYTES, &tmW, &full[stage], (kb0 + kb) * BKE, tap * epi.N + n0);
+              }
+              if (++stage == n_wst) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else
       for (int tile = work_id; tile < num_tiles; tile += work_stride) {
         const int m0 = (tile / n_tiles) * (CTAS * BM) + (int)cta_rank * BM;
         const int n0 = (tile % n_tiles) * BN + (int)cta_rank * (BN / CTAS);
@@ -214,11 +256,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && leader) {   // CTA pair: the leader issues for both CTAs (cta_group::2)
       const uint32_t idesc = make_idesc(CTAS * BM, BN) | (TF32 ? ((2u << 7) | (2u << 10)) : 0u);   // a/b format: F16 = 0, TF32 = 2
       int stage = 0; uint32_t phase = 0;
+      int sstage = 0; uint32_t sphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = work_id; tile < num_tiles; tile += work_stride) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        if (slab) {
+          if constexpr (!TF32) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              mbar_wait(&sfull[sstage], sphase);
+              const uint32_t sa0 = smem_u32(smem + sstage * slab_bytes);
+              for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                // rows of a 128B-swizzled tile are 128 bytes apart and the swizzle is a function of the shared-memory address,
+                // so the tile that starts tap*stride rows into the slab is the slab's descriptor advanced by that many rows
+                const uint32_t sa = sa0 + (uint32_t)(tap * tap_stride) * 128u;
+                const uint32_t sb = smem_u32(wring + stage * C::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = make_desc(sa + k * 32);
+                  const uint64_t db = make_desc(sb + k * 32);
+                  if (CTAS == 2) umma_f16_pair(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  else umma_f16(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+                if (CTAS == 2) tc_commit_pair(&empty[stage]);
+                else tc_commit(&empty[stage]);
+                if (++stage == n_wst) { stage = 0; phase ^= 1; }
+              }
+              if (CTAS == 2) tc_commit_pair(&sempty[sstage]);
+              else tc_commit(&sempty[sstage]);
+              if (++sstage == n_slab) { sstage = 0; sphase ^= 1; }
+            }
+          }
+        } else
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -271,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //             in place and stored.
       //   EPI == 1: fp16-only output, 64 columns per box, one box per warp.
       // Separator rows (row_utt < 0) are written as zeros: they are zero in every rows-layout buffer.
-      constexpr int NB = EPI == 2 ? 3 : 1;
+      constexpr int NB = EPI == 2 ? 3 : (CTAS == 2 ? 2 : 1);
       constexpr int CW = EPI == 2 ? 32 : 64;     // columns per chunk = one 128-byte box row
       constexpr int NCH = BN / CW;               // chunks per tile; this warp takes c = cpar, cpar + 2, ...
       const int ew = warp - 2;
@@ -408,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               pk[k].x = *reinterpret_cast<uint32_t*>(&h0); pk[k].y = *reinterpret_cast<uint32_t*>(&h1);
               pk[k].z = *reinterpret_cast<uint32_t*>(&h2); pk[k].w = *reinterpret_cast<uint32_t*>(&h3);
             }
-            if (lane == 0) bulk_wait_read<0>();            // the previous store has read the (single) box
+            if (lane == 0) bulk_wait_read<NB - 1>();       // the store that last used this box has read it
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ r7) << 4)) = pk[k];
@@ -695,6 +767,21 @@ int g_sm_count = 0;
 int g_debug = -1;   // DTTS_GEMM_DEBUG=1: skip the epilogue (main-loop timing only; results are garbage)
 
 // CTA-pair (cta_group::2) launch: fp16 only, 256 x BN tiles, one 2-CTA cluster per tile stream
+// Slab mode of a multi-tap conv (see the producer): rows of the A slab (multiple of 8, <= 256 = the TMA box limit) and the split
+// of the operand space into n_slab slabs + n_wst weight tiles.  Returns false when the conv keeps the tile-per-tap scheme.
+struct SlabGeo { int rows = 0, bytes = 0, n_slab = 0, n_wst = 0; };
+inline bool slab_geometry(const dtts_gemm_params* p, int space, int b_bytes, SlabGeo* g) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DTTS_GEMM_SLAB"); on = e ? atoi(e) : 1; }
+  if (!on || p->taps < 2 || p->tap_stride < 1) return false;
+  const int rows = (BM + (p->taps - 1) * p->tap_stride + 7) & ~7;
+  if (rows > 256) return false;
+  g->rows = rows; g->bytes = rows * 128; g->n_slab = 2;
+  int n = (space - g->n_slab * g->bytes) / b_bytes;
+  g->n_wst = n > 8 ? 8 : n;
+  return g->n_wst >= 3;
+}
+
 // tensor maps of the TMA epilogues: per-warp boxes of 32 rows x 128 bytes over the output (EPI 1: fp16, EPI 2: fp32) and the
 // fp32 residual.  Unused maps alias the A map (never dereferenced).
 template <int EPI>
@@ -719,7 +806,9 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
     attr_set = true;
   }
   CUtensorMap ma, mw;
-  int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma, 2);
+  SlabGeo sg;
+  const bool use_slab = slab_geometry(p, C::STAGES * C::STAGE_BYTES, C::B_BYTES, &sg);
+  int rc = get_map(p->A, p->M, p->K, p->lda, use_slab ? sg.rows : BM, &ma, 2);
   if (rc) return rc;
   rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN / 2, &mw, 2);
   if (rc) return rc;
@@ -743,7 +832,7 @@ int launch_pair(const dtts_gemm_params* p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = g_dtts_pdl ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, false, 2, GN, EPI>, ma, mw, ma, mw, mo, mr, e, p->K, p->taps, p->tap_shift0, p->tap_stride,
-                                      kb_all, (long)0, g_debug);
+                                      kb_all, (long)0, g_debug, use_slab ? sg.bytes : 0, sg.n_slab, sg.n_wst);
   if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc pair launch failed: %s", cudaGetErrorString(le));
   DTTS_CHECK_LAUNCH("gemm_tc_pair");
   return 0;
@@ -760,7 +849,9 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
   }
   const int es = TF32 ? 4 : 2;
   CUtensorMap ma, mw, ma2, mw2;
-  int rc = get_map(p->A, p->M, p->K, p->lda, BM, &ma, es);
+  SlabGeo sg;
+  const bool use_slab = !TF32 && slab_geometry(p, C::STAGES * C::STAGE_BYTES, C::B_BYTES, &sg);
+  int rc = get_map(p->A, p->M, p->K, p->lda, use_slab ? sg.rows : BM, &ma, es);
   if (rc) return rc;
   rc = get_map(p->W, p->taps * p->N, p->K, p->ldw, BN, &mw, es);
   if (rc) return rc;
@@ -788,7 +879,8 @@ int launch(const dtts_gemm_params* p, cudaStream_t st) {
   dim3 grid(tiles < g_sm_count ? tiles : g_sm_count, splits);
   {
     cudaError_t le = launch_maybe_pdl(gemm_tc_kernel<BN, TF32, 1, GN, EPI>, grid, dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mw, ma2, mw2, mo, mr, e,
-                                      p->K, p->taps, p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug);
+                                      p->K, p->taps, p->tap_shift0, p->tap_stride, kb_per, (long)p->split_stride, g_debug,
+                                      use_slab ? sg.bytes : 0, sg.n_slab, sg.n_wst);
     if (le != cudaSuccess) DTTS_FAIL(-3, "gemm_tc launch failed: %s", cudaGetErrorString(le));
   }
   DTTS_CHECK_LAUNCH("gemm_tc");
