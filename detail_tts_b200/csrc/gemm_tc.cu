@@ -385,6 +385,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return m < epi.M ? (epi.row_utt ? __ldg(epi.row_utt + m) : 0) : -1;
       };
       int utt_next = own_utt(work_id);
+      // ... and the utterance ids of the statistics pass' rows (lane >> 3) + 4 it
+      int uid_next[8];
+      auto stat_utts = [&](int t, int (&u)[8]) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          u[it] = -1;
+          if (GN && epi.row_utt && t < num_tiles) {
+            const int m = (t / n_tiles) * (CTAS * BM) + (int)cta_rank * BM + q * 32 + (lane >> 3) + it * 4;
+            if (m < epi.M) u[it] = __ldg(epi.row_utt + m);
+          }
+        }
+      };
+      stat_utts(work_id, uid_next);
       // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has landed, and the
       // arrive comes from lane 1: lane 0 has TMA stores in flight, and the cluster-scope release of the CTA-pair arrive
       // (MEMBAR + ERRBAR) made it wait for them -- 25 % of the epilogue warps' samples, with the tensor pipe idle behind it.
@@ -403,14 +416,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         utt_next = own_utt(tile + work_stride);
         int uid[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) uid[it] = 0;
-        if (GN && epi.row_utt) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int m = m0 + q * 32 + (lane >> 3) + it * 4;
-            uid[it] = m < epi.M ? __ldg(epi.row_utt + m) : -1;
-          }
-        }
+        for (int it = 0; it < 8; ++it) uid[it] = uid_next[it];
+        stat_utts(tile + work_stride, uid_next);
         int c_last = -1;                             // this warp's last chunk of the tile
         for (int c = cpar; c < NCH && n0 + c * CW < epi.N && debug != 1; c += 2) c_last = c;
         mbar_wait(&tfull[acc], acc_phase);
@@ -491,6 +498,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmO, box, nc, m0 + q * 32);
             bulk_commit();
           }
+          if (has_res) {
+            // refill the box of the PREVIOUS chunk (its store is the older of the two pending groups) with the residual of the
+            // chunk after the next, before the statistics pass below delays it; every lane's reads of that box (the previous
+            // chunk's statistics pass) precede the async write
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            issue_load();
+          }
           if (GN && gn) {
             // statistics of the stored values (fp32 / the fp16-rounded outputs): transposed read of the box, lane = rows
             // (lane >> 3) + 4 it, 16-byte chunk lane & 7 (4 fp32 / 8 fp16 columns, all inside one group: gn_cpg % 8 == 0)
@@ -513,14 +528,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             gn_accumulate(epi.gn_stats, gn_groups, (nc + r7 * (EPI == 2 ? 4 : 8)) / epi.gn_cpg, uid, ps, pss, lane);
           }
           ++use_seq;
-          if (has_res) {
-            // refill the box of the PREVIOUS chunk (its store is the older of the two pending groups) with the residual of the
-            // chunk after the next; every lane's reads of that box (statistics pass) precede the async write
-            if (lane == 0) bulk_wait_read<1>();
-            fence_proxy_async();
-            __syncwarp();
-            issue_load();
-          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -971,13 +978,15 @@ extern "C" int dtts_gemm_f16_tc(const dtts_gemm_params* p, void* stream) {
   int epi = 0;
   if (tma_epi && p->act == DTTS_ACT_NONE && !p->bias_utt && !p->out_row_map && !p->accumulate && (N & 3) == 0 &&
       (!p->bias || (((uintptr_t)p->bias) & 15) == 0) && (g_debug == 0 || g_debug == 1 || g_debug == 2)) {
+    // (fp16 output WITH GroupNorm statistics stays on EPI 0 by default: its statistics pass has to convert the staged fp16 box
+    //  back to fp32 and measured 87 vs 85 us in situ on the c1 convs; DTTS_GEMM_TMAEPI bit 2 forces it for tests)
     if (p->out_f16 && !p->out_f32 && !p->res && p->act16 == DTTS_ACT_NONE && (p->ldo16 & 7) == 0 && (((uintptr_t)p->out_f16) & 15) == 0 &&
-        (!gs || (N & 63) == 0))
+        (!gs || ((N & 63) == 0 && (tma_epi & 4))))
       epi = 1;
     else if (p->out_f32 && !p->out_f16 && (p->ldo32 & 3) == 0 && (((uintptr_t)p->out_f32) & 15) == 0 &&
              (!p->res || ((p->ldr & 3) == 0 && (((uintptr_t)p->res) & 15) == 0)) && (!gs || (N & 31) == 0))
       epi = 2;
-    if (epi & tma_epi) {} else epi = 0;          // DTTS_GEMM_TMAEPI = 0 / 1 / 2 / 3: off / fp16 stores only / fp32 only / both (default)
+    if (epi & tma_epi & 3) {} else epi = 0;          // DTTS_GEMM_TMAEPI = 0 / 1 / 2 / 3: off / fp16 stores only / fp32 only / both (default)
   }
   // the fp32 + residual boxes need 96 KB: a single-CTA 256-wide tile would be left with two operand stages, so those GEMMs
   // take the CTA-pair tile (32 KB stages) whatever their K
