@@ -401,7 +401,7 @@ def gemm_roofline(model, lib, pk):
     # DRAM bytes per launch of the same 62 launches from the committed ncu capture (never measured live under a profiler)
     traffic, traffic_src = None, None
     try:     # the capture is of the 128-utterance eval (71 938 rows incl. separators): only quoted for that shape
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2b_gemm_traffic.json")))
         if tj["launches"] == len(ms) and eng.lay.M == 71938:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:

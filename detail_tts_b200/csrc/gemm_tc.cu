@@ -330,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int cpar = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks c = cpar, cpar+2, ...
     if constexpr (EPI != 0) {
-      // ---------------------------------------------------------------- TMA epilogues (round 3)
+      // ---------------------------------------------------------------- TMA epilogues (round 2, second session)
       // The register/LSU epilogue below moves a 128 x 256 fp32 tile (+ its residual) at ~19 GB/s per SM: ncu shows the epilogue
       // warps parked on the first instruction that reuses an address register of their LDG.128s (the LSU queue is backed up),
       // whatever the number of loads in flight (two-deep register prefetch and an L2 prefetch of the residual tile both
