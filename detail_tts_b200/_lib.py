@@ -200,5 +200,5 @@ def lib():
     """The process-wide library handle (loads on first use; raises if the .so is missing)."""
     global _LIB
     if _LIB is None:
-        _LIB = Lib()
+        _LIB = Lib(os.environ.get("DTTS_LIB") or LIB_PATH)   # DTTS_LIB: an A/B build of the same ABI (development only)
     return _LIB

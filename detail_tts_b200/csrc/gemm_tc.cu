@@ -405,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 1) {
-          if (CTAS == 2) mbar_arrive_leader(&tempty[a]);
+          if (CTAS == 2) mbar_arrive_leader_relaxed(&tempty[a]);
           else mbar_arrive(&tempty[a]);
         }
       };
@@ -716,7 +716,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_leader(&tempty[acc]);   // the leader's issuer waits for both CTAs' epilogues
+        if (CTAS == 2) mbar_arrive_leader_relaxed(&tempty[acc]);   // the leader's issuer waits for both CTAs' epilogues
         else mbar_arrive(&tempty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

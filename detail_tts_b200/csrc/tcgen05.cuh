@@ -134,6 +134,12 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
 }
+// ... without the release fence: for hand-offs that order nothing but TMEM reads already retired by tcgen05.wait::ld (the
+// accumulator-stage release of the GEMM epilogue).  The release form compiles to MEMBAR.ALL + ERRBAR, i.e. the arriving lane waits
+// for every global store it has in flight -- ncu showed 25 % of the epilogue warps' samples there on the CTA-pair tiles.
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+}
 
 // tensor-map cache (host): 2D map over a row-major [rows, cols] matrix (ld elements), box [box_rows, 128 bytes],
 // 128B swizzle; esize 2 = fp16, 4 = fp32.  Defined in gemm_tc.cu.
