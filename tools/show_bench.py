@@ -1,6 +1,6 @@
 import json
 import sys
-for line in sys.stdin:
+for line in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin):   # pass the file name: reading a terminal-less stdin blocks under gpurun
     line = line.strip()
     if not line.startswith("{"):
         continue
