@@ -15,6 +15,8 @@
 // S_t of slot g+2 is issued right after P.V_t of slot g (it reuses that buffer), so the score MMA is never on a
 // warpgroup's critical path; the epilogue of an item (O / l -> HBM) is deferred into the next item's first slot,
 // when its last P.V has long retired.  The [F, F] score matrix never leaves TMEM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -107,6 +109,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// warp-convergent variant (every lane calls it with warp-uniform operands, one elected lane issues: see tcgen05.cuh umma_f16_e)
+__device__ __forceinline__ void umma_f16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -290,7 +302,7 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // Issue order per tile: S_t(0), S_t(1), then for every slot g: wait P_t(g), P.V_t(g), S_t(g+2).  S_t(g+2) reuses
     // the buffer P.V_t(g) has just read (same thread, in order), so the score MMA of the next chunk is never on the
     // softmax warpgroup's critical path, and the three tiles never wait for each other.
-    if (lane == 0) {
+    {                                     // the whole warp runs the issue loop (warp-uniform state), one elected lane issues
       const int t = warp - W_MMA;
       const uint32_t idesc_s = make_idesc(BM, BKV);                       // fp16 x fp16 -> fp32, both K-major
       const uint32_t idesc_o = make_idesc(BM, HD) | (1u << 16);           // B (= V) MN-major
@@ -311,9 +323,9 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         const uint64_t dq = dq0 + (uint64_t)((qb * NT * Q_TILE_BYTES) >> 4), dk = dk0 + (uint64_t)((s_stage * STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16(tm_s + s_buf * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        tc_commit(&s_full[2 * t + s_buf]);
-        if (sn.last_chunk()) { tc_commit(&q_empty[qb]); qb ^= 1; }
+        for (int k = 0; k < HD / 16; ++k) umma_f16_e(tm_s + s_buf * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        tc_commit_e(&s_full[2 * t + s_buf]);
+        if (sn.last_chunk()) { tc_commit_e(&q_empty[qb]); qb ^= 1; }
         if (++s_stage == NS) { s_stage = 0; s_phase ^= 1; }
         s_buf ^= 1;
         sn.next();
@@ -326,9 +338,9 @@ flash48_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint64_t dv = dv0 + (uint64_t)((pv_stage * STAGE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
-          umma_f16_ts(tm_o, tm_s + pv_buf * BKV + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (pv.c > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&o_full[t]);
-        tc_commit(&kv_empty[pv_stage]);                                   // 3 arrivals (one per tile) free the stage
+          umma_f16_ts_e(tm_o, tm_s + pv_buf * BKV + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (pv.c > 0 || k > 0) ? 1u : 0u);
+        tc_commit_e(&o_full[t]);
+        tc_commit_e(&kv_empty[pv_stage]);                                   // 3 arrivals (one per tile) free the stage
         if (sn.valid) issue_s();
         if (++pv_stage == NS) pv_stage = 0;
         pv_buf ^= 1;

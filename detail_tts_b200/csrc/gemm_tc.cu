@@ -253,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    if (lane == 0 && leader) {   // CTA pair: the leader issues for both CTAs (cta_group::2)
+    if (leader) {   // CTA pair: the leader issues for both CTAs (cta_group::2).  The WHOLE warp runs the loop (warp-uniform
+                    // operands, one elected lane issues: see umma_f16_e)
       const uint32_t idesc = make_idesc(CTAS * BM, BN) | (TF32 ? ((2u << 7) | (2u << 10)) : 0u);   // a/b format: F16 = 0, TF32 = 2
       int stage = 0; uint32_t phase = 0;
       int sstage = 0; uint32_t sphase = 0;
@@ -278,15 +279,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t da = make_desc(sa + k * 32);
                   const uint64_t db = make_desc(sb + k * 32);
-                  if (CTAS == 2) umma_f16_pair(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                  else umma_f16(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  if (CTAS == 2) umma_f16_pair_e(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  else umma_f16_e(d_tmem, da, db, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
                 }
-                if (CTAS == 2) tc_commit_pair(&empty[stage]);
-                else tc_commit(&empty[stage]);
+                if (CTAS == 2) tc_commit_pair_e(&empty[stage]);
+                else tc_commit_e(&empty[stage]);
                 if (++stage == n_wst) { stage = 0; phase ^= 1; }
               }
-              if (CTAS == 2) tc_commit_pair(&sempty[sstage]);
-              else tc_commit(&sempty[sstage]);
+              if (CTAS == 2) tc_commit_pair_e(&sempty[sstage]);
+              else tc_commit_e(&sempty[sstage]);
               if (++sstage == n_slab) { sstage = 0; sphase ^= 1; }
             }
           }
@@ -301,8 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {   // 4 x (K=16 fp16 = 32 B)
               const uint64_t da = make_desc(sa + k * 32);
               const uint64_t db = make_desc(sb + k * 32);
-              if (CTAS == 2) umma_f16_pair(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-              else umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              if (CTAS == 2) umma_f16_pair_e(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              else umma_f16_e(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           } else {
             const uint32_t sa2 = sb + C::B_BYTES, sb2 = sa2 + A_BYTES;
@@ -311,16 +312,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t xa = seg == 1 ? sa2 : sa, xb = seg == 2 ? sb2 : sb;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {   // 4 x (K=8 tf32 = 32 B)
-                umma_tf32(d_tmem, make_desc(xa + k * 32), make_desc(xb + k * 32), idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
+                umma_tf32_e(d_tmem, make_desc(xa + k * 32), make_desc(xb + k * 32), idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
               }
             }
           }
-          if (CTAS == 2) tc_commit_pair(&empty[stage]);   // multicast: frees the slot in both CTAs
-          else tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (CTAS == 2) tc_commit_pair_e(&empty[stage]);   // multicast: frees the slot in both CTAs
+          else tc_commit_e(&empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CTAS == 2) tc_commit_pair(&tfull[acc]);
-        else tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
+        if (CTAS == 2) tc_commit_pair_e(&tfull[acc]);
+        else tc_commit_e(&tfull[acc]);      // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
