@@ -179,7 +179,7 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ C
     // One thread issues ~55 clocks per tcgen05.mma (descriptor arithmetic + election), far more than a narrow-N MMA takes to
     // execute: NACC issuer threads take alternate K blocks into their own TMEM accumulators (summed by the epilogue).
     const int me = warp - 1;
-    if (lane == 0 && me < C::NACC) {
+    if (me < C::NACC) {          // the whole warp runs the issue loop with warp-uniform operands; one elected lane issues (umma_tf32_e)
       const uint32_t idesc2 = make_idesc(128, 2 * BP) | (2u << 7) | (2u << 10);   // a/b format TF32, N = 2*BP: [x_hi ; x_lo]
       const uint32_t idesc1 = make_idesc(128, BP) | (2u << 7) | (2u << 10);       // N = BP: x_hi only
       const uint32_t acc = tmem_base + (uint32_t)(me * 2 * BP);
@@ -187,23 +187,23 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ C
       for (int kb = 0; kb < nkb; ++kb) {
         if (kb % C::NACC == me) {
           mbar_wait(&full_w[s], ph);
-          if (me == 0) TR(16 + kb * 8 + 1);
+          if (me == 0 && lane == 0) TR(16 + kb * 8 + 1);
           mbar_wait(&full_x[s], ph);
-          if (me == 0) TR(16 + kb * 8 + 2);
+          if (me == 0 && lane == 0) TR(16 + kb * 8 + 2);
           tc_fence_after();
           const uint32_t w_hi = smem_u32(smem + s * C::STAGE_BYTES);
           const uint64_t d_whi = make_desc(w_hi), d_wlo = make_desc(w_hi + W_TILE_BYTES), d_x = make_desc(w_hi + 2 * W_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {       // 4 x (K = 8 tf32 = 32 bytes: +2 in the descriptor's 16-byte address units)
-            umma_tf32(acc, d_whi + 2 * k, d_x + 2 * k, idesc2, (kb >= C::NACC || k > 0) ? 1u : 0u);   // W_hi*x_hi | W_hi*x_lo
-            umma_tf32(acc + BP, d_wlo + 2 * k, d_x + 2 * k, idesc1, 1u);                              // += W_lo*x_hi
+            umma_tf32_e(acc, d_whi + 2 * k, d_x + 2 * k, idesc2, (kb >= C::NACC || k > 0) ? 1u : 0u);   // W_hi*x_hi | W_hi*x_lo
+            umma_tf32_e(acc + BP, d_wlo + 2 * k, d_x + 2 * k, idesc1, 1u);                              // += W_lo*x_hi
           }
-          tc_commit(&empty[s]);
-          if (me == 0) TR(16 + kb * 8 + 3);
+          tc_commit_e(&empty[s]);
+          if (me == 0 && lane == 0) TR(16 + kb * 8 + 3);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
       }
-      tc_commit(acc_full);
+      tc_commit_e(acc_full);
     }
     __syncwarp();
     if (csize > 1) { cluster_wait(); cluster_sync_all(); } else __syncthreads();     // (see the epilogue warps)
