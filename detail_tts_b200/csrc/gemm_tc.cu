@@ -399,9 +399,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       stat_utts(work_id, uid_next);
-      // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has landed, and the
-      // arrive comes from lane 1: lane 0 has TMA stores in flight, and the cluster-scope release of the CTA-pair arrive
-      // (MEMBAR + ERRBAR) made it wait for them -- 25 % of the epilogue warps' samples, with the tensor pipe idle behind it.
+      // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has landed.  The arrive
+      // is fence-free on the CTA-pair tiles (mbar_arrive_leader_relaxed) and comes from lane 1, which has no TMA stores in flight:
+      // with the cluster-scope RELEASE arrive from lane 0 (MEMBAR + ERRBAR) the lane waited for its own stores -- 25 % of the
+      // epilogue warps' samples, with the tensor pipe idle behind it.
       auto release_acc = [&](int a) {
         tc_fence_before();
         __syncwarp();
