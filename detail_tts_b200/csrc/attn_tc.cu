@@ -104,15 +104,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// warp-convergent variant (every lane calls it with warp-uniform operands, one elected lane issues: see tcgen05.cuh umma_f16_e)
+// P.V: A operand from TMEM.  Warp-convergent issue (every lane calls it with warp-uniform operands, one elected lane issues: see
+// tcgen05.cuh umma_f16_e)
 __device__ __forceinline__ void umma_f16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\t"
