@@ -46,7 +46,9 @@ typedef struct {
   int tap_stride;       /* row shift increment per tap (dilation) */
   const float* bias;      /* [N] or NULL */
   const float* bias_utt;  /* [n_utt, N] per-utterance bias or NULL (needs row_utt) */
-  const int* row_utt;     /* [M]: utterance id, or -1 => row is a separator (not stored); NULL = all valid */
+  const int* row_utt;     /* [M]: utterance id, or -1 => row is a separator: not stored by the register epilogues, stored as
+                           * ZEROS by the TMA epilogues of dtts_gemm_f16_tc (separator rows are zero in every rows-layout buffer);
+                           * NULL = all valid */
   const int* out_row_map; /* [M]: output/residual row index for A row m; NULL = identity */
   const float* res;       /* fp32 residual [*, Nout], ldr; added after the activation; NULL = none */
   float* out_f32;         /* fp32 output [*, Nout], ldo32; NULL = none */
